@@ -1,0 +1,89 @@
+"""Device plumbing: NumPy / torch in, device tensor through the kernels, same kind out.
+
+PyTorch is used for device memory and streams only; every computation on the
+state happens in libffsim_b200.so.
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+import torch
+
+from ffsim_b200 import _lib
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "ffsim_b200 needs a CUDA device: the state-vector kernels are sm_100a CUDA "
+            "and there is no CPU fallback."
+        )
+
+
+def sync_device() -> int:
+    """Make torch's current device the C library's current device; return its index."""
+    dev = torch.cuda.current_device()
+    _lib.check(_lib.lib.ffb_set_device(dev))
+    return dev
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Kind:
+    """How the caller handed the vector over, so that it gets the same kind back."""
+
+    __slots__ = ("numpy", "torch_cpu", "device")
+
+    def __init__(self, numpy=False, torch_cpu=False, device=None):
+        self.numpy = numpy
+        self.torch_cpu = torch_cpu
+        self.device = device
+
+
+def to_device(vec: Any, *, copy: bool) -> tuple[torch.Tensor, Kind]:
+    """1-D complex128 CUDA tensor holding ``vec``.
+
+    NumPy arrays and CPU tensors are uploaded (so the result never aliases the
+    input); CUDA tensors are cloned only when ``copy`` is set.
+    """
+    require_cuda()
+    if isinstance(vec, torch.Tensor):
+        if vec.is_cuda:
+            with torch.cuda.device(vec.device):
+                t = vec.reshape(-1)
+                if t.dtype != torch.complex128:
+                    t = t.to(torch.complex128)
+                elif copy or not t.is_contiguous():
+                    t = t.clone(memory_format=torch.contiguous_format)
+            return t, Kind(device=vec.device)
+        t = vec.reshape(-1).to(torch.complex128).contiguous()
+        return t.cuda(non_blocking=False), Kind(torch_cpu=True)
+    arr = np.ascontiguousarray(np.asarray(vec).reshape(-1), dtype=np.complex128)
+    return torch.from_numpy(arr).cuda(), Kind(numpy=True)
+
+
+def from_device(t: torch.Tensor, kind: Kind):
+    if kind.numpy:
+        return t.cpu().numpy()
+    if kind.torch_cpu:
+        return t.cpu()
+    return t
+
+
+def new_like(t: torch.Tensor) -> torch.Tensor:
+    return torch.empty_like(t)
+
+
+def is_device_vector(vec: Any) -> bool:
+    return isinstance(vec, torch.Tensor) and vec.is_cuda
+
+
+def as_host_matrix(mat: Any, dtype=None) -> np.ndarray:
+    """Small operator matrices live on the host (norb x norb)."""
+    if isinstance(mat, torch.Tensor):
+        mat = mat.detach().cpu().numpy()
+    return np.asarray(mat) if dtype is None else np.asarray(mat, dtype=dtype)

@@ -1,0 +1,326 @@
+// Diagonal operators for sm_100a: diagonal-Coulomb and number-operator-sum
+// evolution (phase multiply) and contraction (real coefficient multiply).
+//
+// One warp owns one alpha row at a time.  For the alpha-beta coupling it first
+// builds, in shared memory, the row's per-orbital factors
+//     pm[j] = prod_{i in occ(a)} M_ab[i][j]              (number representation)
+// (the `phase_map` row of src/gates/diag_coulomb.rs:61-75) and from them one
+// lookup table per 8-orbital chunk of the beta string, so that an amplitude
+// costs one table gather per chunk instead of one multiply per occupied
+// orbital.  The row is then streamed once: 16 B read + 16 B write per amplitude.
+// The z representation (diag_coulomb.rs:95-190) only changes how the tables are
+// filled (conjugate / sign selected by the string bits over all orbitals).
+#include <cuda_runtime.h>
+
+#include "kernels.hpp"
+
+namespace ffb {
+
+namespace {
+
+struct Cx {
+  using T = double2;
+  static __device__ __forceinline__ T one() { return make_double2(1.0, 0.0); }
+  static __device__ __forceinline__ T comb(T a, T b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  }
+  static __device__ __forceinline__ T flip(T a) { return make_double2(a.x, -a.y); }  // conj
+};
+struct Re {
+  using T = double;
+  static __device__ __forceinline__ T one() { return 0.0; }
+  static __device__ __forceinline__ T comb(T a, T b) { return a + b; }
+  static __device__ __forceinline__ T flip(T a) { return -a; }
+};
+
+// factor of one string from a same-spin matrix
+//   number rep: comb over occupied pairs j <= k of M[o_j][o_k]
+//   z rep:      comb over all j < k of (bit_j != bit_k ? flip(M[j][k]) : M[j][k])
+// In the real (contraction) semiring flip is negation, which is exactly the
+// sign product z_j z_k of src/contract/diag_coulomb.rs:100-174.
+template <class S>
+__global__ void side_factor_kernel(const uint32_t *__restrict__ strings, long long dim, int norb,
+                                   const typename S::T *__restrict__ mat, int zrep,
+                                   typename S::T *__restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < dim;
+       r += (long long)gridDim.x * blockDim.x) {
+    const uint32_t s = strings[r];
+    typename S::T acc = S::one();
+    if (!zrep) {
+      uint32_t sj = s;
+      while (sj) {
+        const int j = __ffs(sj) - 1;
+        uint32_t sk = sj;  // k >= j
+        while (sk) {
+          const int k = __ffs(sk) - 1;
+          sk &= sk - 1;
+          acc = S::comb(acc, mat[j * norb + k]);
+        }
+        sj &= sj - 1;
+      }
+    } else {
+      for (int j = 0; j < norb; ++j)
+        for (int k = j + 1; k < norb; ++k) {
+          const typename S::T m = mat[j * norb + k];
+          acc = S::comb(acc, (((s >> j) ^ (s >> k)) & 1u) ? S::flip(m) : m);
+        }
+    }
+    out[r] = acc;
+  }
+}
+
+struct DiagParams {
+  const uint32_t *strings_a;
+  const uint32_t *strings_b;
+  const void *rowfac;  // [dim_a] or NULL
+  const void *colfac;  // [dim_b] or NULL
+  const void *mab;     // [norb*norb] or NULL
+  const double2 *vec;
+  double2 *out;
+  long long row0, n_rows, dim_b;
+  int norb, zrep, accumulate;
+};
+
+template <class S, bool CONTRACT>
+__global__ void __launch_bounds__(256) diag_kernel(const DiagParams p) {
+  using T = typename S::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int nch = (p.norb + 7) >> 3;
+  T *pm = reinterpret_cast<T *>(smem_raw) + (size_t)warp * (32 + nch * 256);
+  T *tab = pm + 32;
+  const T *__restrict__ rowfac = reinterpret_cast<const T *>(p.rowfac);
+  const T *__restrict__ colfac = reinterpret_cast<const T *>(p.colfac);
+  const T *__restrict__ mab = reinterpret_cast<const T *>(p.mab);
+  const long long gw = (long long)blockIdx.x * wpb + warp, nw = (long long)gridDim.x * wpb;
+
+  for (long long row = gw; row < p.n_rows; row += nw) {
+    const uint32_t a = p.strings_a[p.row0 + row];
+    const T rf = rowfac ? rowfac[p.row0 + row] : S::one();
+    if (mab) {
+      for (int j = lane; j < p.norb; j += 32) {
+        T acc = S::one();
+        for (int i = 0; i < p.norb; ++i) {
+          const bool bit = (a >> i) & 1u;
+          const T m = mab[i * p.norb + j];
+          if (p.zrep)
+            acc = S::comb(acc, bit ? S::flip(m) : m);
+          else if (bit)
+            acc = S::comb(acc, m);
+        }
+        pm[j] = acc;
+      }
+      __syncwarp();
+      for (int c = 0; c < nch; ++c) {
+        const int nb = min(8, p.norb - 8 * c);
+        for (int e = lane; e < (1 << nb); e += 32) {
+          T acc = (c == 0) ? rf : S::one();
+          for (int j = 0; j < nb; ++j) {
+            const bool bit = (e >> j) & 1;
+            const T m = pm[8 * c + j];
+            if (p.zrep)
+              acc = S::comb(acc, bit ? S::flip(m) : m);
+            else if (bit)
+              acc = S::comb(acc, m);
+          }
+          tab[c * 256 + e] = acc;
+        }
+      }
+      __syncwarp();
+    }
+    const double2 *__restrict__ src = p.vec + row * p.dim_b;
+    double2 *__restrict__ dst = p.out + row * p.dim_b;
+#pragma unroll 4
+    for (long long b = lane; b < p.dim_b; b += 32) {
+      const uint32_t s = p.strings_b[b];
+      T f = colfac ? colfac[b] : S::one();
+      if (mab) {
+        f = S::comb(f, tab[s & 255u]);
+        for (int c = 1; c < nch; ++c) f = S::comb(f, tab[c * 256 + ((s >> (8 * c)) & 255u)]);
+      } else {
+        f = S::comb(f, rf);
+      }
+      const double2 v = src[b];
+      if constexpr (CONTRACT) {
+        double2 o = make_double2(f * v.x, f * v.y);
+        if (p.accumulate) {
+          const double2 old = dst[b];
+          o.x += old.x;
+          o.y += old.y;
+        }
+        dst[b] = o;
+      } else {
+        dst[b] = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void vdot_kernel(const double2 *__restrict__ x, const double2 *__restrict__ y,
+                            long long n, double *__restrict__ partial) {
+  double ar = 0.0, ai = 0.0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const double2 a = x[e], b = y[e];
+    ar += a.x * b.x + a.y * b.y;  // conj(a) * b
+    ai += a.x * b.y - a.y * b.x;
+  }
+  __shared__ double sr[32], si[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sr[warp] = ar;
+    si[warp] = ai;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nwp = blockDim.x >> 5;
+    ar = lane < nwp ? sr[lane] : 0.0;
+    ai = lane < nwp ? si[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      ar += __shfl_xor_sync(0xffffffffu, ar, o);
+      ai += __shfl_xor_sync(0xffffffffu, ai, o);
+    }
+    if (lane == 0) {
+      partial[2 * blockIdx.x] = ar;
+      partial[2 * blockIdx.x + 1] = ai;
+    }
+  }
+}
+
+__global__ void vdot_final_kernel(const double *__restrict__ partial, int n_blocks,
+                                  double *__restrict__ result) {
+  // fixed-order tree over the block partials: deterministic
+  __shared__ double sr[256], si[256];
+  double ar = 0.0, ai = 0.0;
+  for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) {
+    ar += partial[2 * i];
+    ai += partial[2 * i + 1];
+  }
+  sr[threadIdx.x] = ar;
+  si[threadIdx.x] = ai;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sr[threadIdx.x] += sr[threadIdx.x + o];
+      si[threadIdx.x] += si[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    result[0] = sr[0];
+    result[1] = si[0];
+  }
+}
+
+__global__ void axpby_kernel(double ar, double ai, const double2 *__restrict__ x, double br,
+                             double bi, double2 *__restrict__ y, long long n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const double2 a = x[e];
+    double2 r = make_double2(ar * a.x - ai * a.y, ar * a.y + ai * a.x);
+    if (br != 0.0 || bi != 0.0) {
+      const double2 b = y[e];
+      r.x += br * b.x - bi * b.y;
+      r.y += br * b.y + bi * b.x;
+    }
+    y[e] = r;
+  }
+}
+
+int grid_1d(long long total, int threads, int sm_count, int per_sm) {
+  long long blocks = (total + threads - 1) / threads;
+  long long cap = (long long)sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+cudaError_t launch_side_factor(bool contract, const uint32_t *strings, long long dim, int norb,
+                               const void *mat, int zrep, void *out, int sm_count,
+                               cudaStream_t stream) {
+  if (dim <= 0) return cudaSuccess;
+  const int grid = grid_1d(dim, 128, sm_count, 16);
+  if (contract)
+    side_factor_kernel<Re><<<grid, 128, 0, stream>>>(strings, dim, norb, (const double *)mat, zrep,
+                                                     (double *)out);
+  else
+    side_factor_kernel<Cx><<<grid, 128, 0, stream>>>(strings, dim, norb, (const double2 *)mat,
+                                                     zrep, (double2 *)out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t *strings_b,
+                        const void *rowfac, const void *colfac, const void *mab, const void *vec,
+                        void *out, long long row0, long long n_rows, long long dim_b, int norb,
+                        int zrep, int accumulate, int sm_count, cudaStream_t stream) {
+  if (n_rows <= 0 || dim_b <= 0) return cudaSuccess;
+  DiagParams p;
+  p.strings_a = strings_a;
+  p.strings_b = strings_b;
+  p.rowfac = rowfac;
+  p.colfac = colfac;
+  p.mab = mab;
+  p.vec = (const double2 *)vec;
+  p.out = (double2 *)out;
+  p.row0 = row0;
+  p.n_rows = n_rows;
+  p.dim_b = dim_b;
+  p.norb = norb;
+  p.zrep = zrep;
+  p.accumulate = accumulate;
+  const int threads = 256, wpb = threads / 32;
+  const int nch = (norb + 7) / 8;
+  const size_t elem = contract ? sizeof(double) : sizeof(double2);
+  const size_t smem = mab ? (size_t)wpb * (32 + nch * 256) * elem : 0;
+  long long blocks = (n_rows + wpb - 1) / wpb;
+  const long long cap = (long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  cudaError_t e = cudaSuccess;
+  if (contract) {
+    static size_t conf = 48 * 1024;
+    if (smem > conf) {
+      e = cudaFuncSetAttribute(diag_kernel<Re, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem);
+      if (e != cudaSuccess) return e;
+      conf = smem;
+    }
+    diag_kernel<Re, true><<<(int)blocks, threads, smem, stream>>>(p);
+  } else {
+    static size_t conf = 48 * 1024;
+    if (smem > conf) {
+      e = cudaFuncSetAttribute(diag_kernel<Cx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem);
+      if (e != cudaSuccess) return e;
+      conf = smem;
+    }
+    diag_kernel<Cx, false><<<(int)blocks, threads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vdot(const void *x, const void *y, long long n, void *partial, int n_partial,
+                        void *result, int sm_count, cudaStream_t stream) {
+  int grid = grid_1d(n, 256, sm_count, 8);
+  if (grid > n_partial) grid = n_partial;
+  vdot_kernel<<<grid, 256, 0, stream>>>((const double2 *)x, (const double2 *)y, n,
+                                        (double *)partial);
+  vdot_final_kernel<<<1, 256, 0, stream>>>((const double *)partial, grid, (double *)result);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_axpby(double ar, double ai, const void *x, double br, double bi, void *y,
+                         long long n, int sm_count, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  axpby_kernel<<<grid_1d(n, 256, sm_count, 8), 256, 0, stream>>>(ar, ai, (const double2 *)x, br,
+                                                                 bi, (double2 *)y, n);
+  return cudaGetLastError();
+}
+
+}  // namespace ffb

@@ -1,0 +1,416 @@
+// Givens-rotation kernels for sm_100a.
+//
+//  * fused_pass_kernel<w>: one sweep over the state.  A CTA stages a tile
+//    (C(W,m) string addresses x `cols` batch columns, complex128) in shared
+//    memory, applies every rotation of the pass to it in sub-passes whose
+//    rotations stay inside a register block of w orbitals (up to C(6,3) = 20
+//    amplitudes per thread, statically unrolled), and writes the tile back.
+//    HBM traffic per pass: each amplitude read once and written once (32 B),
+//    however many rotations the pass fuses.
+//  * givens_single_kernel / phase_shift_kernel: one launch per rotation, the
+//    arithmetic of src/gates/orbital_rotation.rs:86-104 and
+//    src/gates/phase_shift.rs:18-30 -- the _lib-level entry points and the
+//    correctness anchor for the fused path.
+//  * row_scale_kernel, transpose_kernel: helpers.
+#include <cuda_runtime.h>
+
+#include "device_structs.h"
+#include "kernels.hpp"
+
+namespace ffb {
+
+// ---------------------------------------------------------------- constexpr combinatorics
+__host__ __device__ constexpr int cbinom(int n, int k) {
+  if (k < 0 || k > n) return 0;
+  long long r = 1;
+  for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+  return (int)r;
+}
+__host__ __device__ constexpr int cpopc(unsigned s) {
+  int c = 0;
+  while (s) {
+    c += s & 1u;
+    s >>= 1;
+  }
+  return c;
+}
+// colexicographic rank of s among strings with the same popcount
+__host__ __device__ constexpr int crank(unsigned s) {
+  int r = 0, idx = 0, pos = 0;
+  while (s) {
+    if (s & 1u) r += cbinom(pos, ++idx);
+    s >>= 1;
+    ++pos;
+  }
+  return r;
+}
+__host__ __device__ constexpr int cclass_offset(int w, int mp) {
+  int off = 0;
+  for (int j = 1; j < mp; ++j) off += cbinom(w, j);
+  return off;
+}
+
+// ---------------------------------------------------------------- the 2x2 update
+// x' = c x + s y ; y' = c y - conj(s) x      (12 DFMA-pipe operations)
+__device__ __forceinline__ void zrot(double2 &x, double2 &y, double c, double sr, double si) {
+  const double xr = x.x, xi = x.y, yr = y.x, yi = y.y;
+  x.x = fma(-si, yi, fma(sr, yr, c * xr));
+  x.y = fma(si, yr, fma(sr, yi, c * xi));
+  y.x = fma(-si, xi, fma(-sr, xr, c * yr));
+  y.y = fma(si, xr, fma(-sr, xi, c * yi));
+}
+
+// all (x, y) pairs of a W-orbital, M-electron register block for the rotation
+// on block-relative orbitals (Q, Q+1); statically unrolled
+template <int W, int M, int Q, int S = 0>
+__device__ __forceinline__ void rot_block(double2 (&a)[cbinom(W, M)], double c, double sr,
+                                          double si) {
+  if constexpr (S < (1 << W)) {
+    if constexpr (cpopc(S) == M && ((S >> Q) & 3) == 1) {
+      zrot(a[crank(S)], a[crank(S ^ (3 << Q))], c, sr, si);
+    }
+    rot_block<W, M, Q, S + 1>(a, c, sr, si);
+  }
+}
+
+template <int W, int M, int Q = 0>
+__device__ __forceinline__ void rot_dispatch(double2 (&a)[cbinom(W, M)], int q, double c,
+                                             double sr, double si) {
+  if constexpr (Q < W - 1) {
+    if (q == Q)
+      rot_block<W, M, Q>(a, c, sr, si);
+    else
+      rot_dispatch<W, M, Q + 1>(a, q, c, sr, si);
+  }
+}
+
+// One register block: gather, rotate, scatter.
+template <int W, int M>
+__device__ __forceinline__ void process_item(double2 *__restrict__ tile, int cols, int col,
+                                             uint32_t entry, const uint16_t *__restrict__ offtab,
+                                             const PassParams &p, int r0, int r1, int q0) {
+  constexpr int N = cbinom(W, M);
+  const int base = (int)(entry & 0xFFFFFFu);
+  const uint16_t *o = offtab + (entry >> 24) * kOffRow + cclass_offset(W, M);
+  double2 a[N];
+  int idx[N];
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    idx[t] = (base + (int)o[t]) * cols + col;
+    a[t] = tile[idx[t]];
+  }
+  for (int r = r0; r < r1; ++r) {
+    rot_dispatch<W, M>(a, (int)p.rq[r] - q0, p.rc[r], p.rsr[r], p.rsi[r]);
+  }
+#pragma unroll
+  for (int t = 0; t < N; ++t) tile[idx[t]] = a[t];
+}
+
+template <int W, int M = 1>
+__device__ __forceinline__ void process_dispatch(int mp, double2 *tile, int cols, int col,
+                                                 uint32_t entry, const uint16_t *offtab,
+                                                 const PassParams &p, int r0, int r1, int q0) {
+  if constexpr (M < W) {
+    if (mp == M)
+      process_item<W, M>(tile, cols, col, entry, offtab, p, r0, r1, q0);
+    else
+      process_dispatch<W, M + 1>(mp, tile, cols, col, entry, offtab, p, r0, r1, q0);
+  }
+}
+
+constexpr int kOffTabEntries = kMaxLowDev * kOffRow;  // u16 entries of one sub-pass table
+
+template <int W>
+__global__ void __launch_bounds__(512, 1)
+    fused_pass_kernel(const __grid_constant__ PassParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t *offbuf = reinterpret_cast<uint16_t *>(smem_raw);  // 2 x kOffTabEntries
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw + 2 * kOffTabEntries * sizeof(uint16_t));
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  double2 *__restrict__ data = reinterpret_cast<double2 *>(p.data);
+  const double2 *__restrict__ rowphase = reinterpret_cast<const double2 *>(p.rowphase);
+
+  for (long long unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+    int gi = 0;
+    while (gi + 1 < p.n_groups && unit >= p.g[gi + 1].unit_begin) ++gi;
+    const GroupLaunch &G = p.g[gi];
+    const long long local = unit - G.unit_begin;
+    const long long combo = local / G.n_strips;
+    const long long strip = local - combo * G.n_strips;
+    const int R = G.R, cols = G.cols;
+    const long long col0 = strip * cols;
+    const int ncv = (int)min((long long)cols, p.n_cols - col0);
+    const uint32_t rowbase = p.u32[G.combo_base_off + combo];
+    const uint32_t *__restrict__ tab =
+        p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
+    const int n_el = R * cols;
+
+    // ---- load the tile
+    if (p.col_stride == 1) {
+      for (int e = tid; e < n_el; e += nthr) {
+        const int r = e / cols, j = e - r * cols;
+        double2 v = make_double2(0.0, 0.0);
+        if (j < ncv) v = data[(long long)(rowbase + tab[r]) * p.row_stride + col0 + j];
+        tile[e] = v;
+      }
+    } else {
+      for (int e = tid; e < n_el; e += nthr) {
+        const int j = e / R, r = e - j * R;
+        double2 v = make_double2(0.0, 0.0);
+        if (j < ncv)
+          v = data[(long long)(rowbase + tab[r]) * p.row_stride + (col0 + j) * p.col_stride];
+        tile[r * cols + j] = v;
+      }
+    }
+    if (G.has_blocks && p.n_sub > 0) {
+      for (int e = tid; e < kOffTabEntries / 2; e += nthr)
+        reinterpret_cast<uint32_t *>(offbuf)[e] = reinterpret_cast<const uint32_t *>(p.off)[e];
+    }
+    __syncthreads();
+
+    // ---- sub-passes
+    if (G.has_blocks) {
+      for (int s = 0; s < p.n_sub; ++s) {
+        const uint16_t *offtab = offbuf + (s & 1) * kOffTabEntries;
+        if (s + 1 < p.n_sub) {  // prefetch the next sub-pass's offset table
+          uint32_t *dst = reinterpret_cast<uint32_t *>(offbuf + ((s + 1) & 1) * kOffTabEntries);
+          const uint32_t *src =
+              reinterpret_cast<const uint32_t *>(p.off + (size_t)(s + 1) * kOffTabEntries);
+          for (int e = tid; e < kOffTabEntries / 2; e += nthr) dst[e] = src[e];
+        }
+        const GroupSubDev &gs = p.gsub[G.gsub_off + s];
+        const int q0 = p.sub[s].q0, r0 = p.sub[s].rot_begin, r1 = p.sub[s].rot_end;
+        const uint32_t *__restrict__ blocks = p.u32 + gs.blocks_off;
+        int chunk_base = 0;
+        for (int sg = 0; sg < gs.n_seg; ++sg) {
+          const int mp = gs.seg[sg].mp, n_items = gs.seg[sg].count * cols;
+          const int n_chunks = (n_items + 31) >> 5;
+          // warps take 32-item chunks round-robin over the concatenated chunk list
+          int first = (warp - chunk_base % nwarp + nwarp) % nwarp;
+          for (int ch = first; ch < n_chunks; ch += nwarp) {
+            const int item = (ch << 5) + lane;
+            if (item < n_items) {
+              const int blk = item / cols, col = item - blk * cols;
+              const uint32_t entry = blocks[gs.seg[sg].begin + blk];
+              process_dispatch<W>(mp, tile, cols, col, entry, offtab, p, r0, r1, q0);
+            }
+          }
+          chunk_base += n_chunks;
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- store the tile (and fold the per-row phase product in on the last pass)
+    if (p.col_stride == 1) {
+      for (int e = tid; e < n_el; e += nthr) {
+        const int r = e / cols, j = e - r * cols;
+        if (j < ncv) {
+          double2 v = tile[e];
+          const uint32_t row = rowbase + tab[r];
+          if (rowphase) {
+            const double2 f = rowphase[row];
+            v = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+          }
+          data[(long long)row * p.row_stride + col0 + j] = v;
+        }
+      }
+    } else {
+      for (int e = tid; e < n_el; e += nthr) {
+        const int j = e / R, r = e - j * R;
+        if (j < ncv) {
+          double2 v = tile[r * cols + j];
+          const uint32_t row = rowbase + tab[r];
+          if (rowphase) {
+            const double2 f = rowphase[row];
+            v = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+          }
+          data[(long long)row * p.row_stride + (col0 + j) * p.col_stride] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int W>
+static cudaError_t launch_w(const PassParams &p, int grid, int threads, size_t smem,
+                            cudaStream_t stream) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(fused_pass_kernel<W>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  fused_pass_kernel<W><<<grid, threads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+size_t fused_pass_smem_overhead() { return 2 * kOffTabEntries * sizeof(uint16_t); }
+
+cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t tile_bytes,
+                              cudaStream_t stream) {
+  size_t smem = tile_bytes + fused_pass_smem_overhead();
+  switch (p.w) {
+    case 2: return launch_w<2>(p, grid, threads, smem, stream);
+    case 3: return launch_w<3>(p, grid, threads, smem, stream);
+    case 4: return launch_w<4>(p, grid, threads, smem, stream);
+    case 5: return launch_w<5>(p, grid, threads, smem, stream);
+    case 6: return launch_w<6>(p, grid, threads, smem, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---------------------------------------------------------------- one rotation per launch
+__global__ void givens_single_kernel(double2 *__restrict__ vec, long long ld, long long dim_b,
+                                     double c, double sr, double si,
+                                     const unsigned long long *__restrict__ s1,
+                                     const unsigned long long *__restrict__ s2, long long n_pairs) {
+  const long long total = n_pairs * dim_b;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long k = e / dim_b, col = e - k * dim_b;
+    double2 *px = vec + (long long)s1[k] * ld + col;
+    double2 *py = vec + (long long)s2[k] * ld + col;
+    double2 x = *px, y = *py;
+    zrot(x, y, c, sr, si);
+    *px = x;
+    *py = y;
+  }
+}
+
+__global__ void phase_shift_kernel(double2 *__restrict__ vec, long long ld, long long dim_b,
+                                   double pr, double pi,
+                                   const unsigned long long *__restrict__ indices, long long n) {
+  const long long total = n * dim_b;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long k = e / dim_b, col = e - k * dim_b;
+    double2 *px = vec + (long long)indices[k] * ld + col;
+    const double2 x = *px;
+    *px = make_double2(x.x * pr - x.y * pi, x.x * pi + x.y * pr);
+  }
+}
+
+// vec[row, :] *= phase[row]   (row stride ld, n_cols columns; or the strided variant)
+__global__ void row_scale_kernel(double2 *__restrict__ vec, long long n_rows, long long n_cols,
+                                 long long row_stride, long long col_stride,
+                                 const double2 *__restrict__ phase) {
+  const long long total = n_rows * n_cols;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    long long row, col;
+    if (col_stride == 1) {
+      row = e / n_cols;
+      col = e - row * n_cols;
+    } else {
+      col = e / n_rows;
+      row = e - col * n_rows;
+    }
+    double2 *px = vec + row * row_stride + col * col_stride;
+    const double2 x = *px, f = phase[row];
+    *px = make_double2(x.x * f.x - x.y * f.y, x.x * f.y + x.y * f.x);
+  }
+}
+
+// phase[row] = prod_{i in string(row)} orbital_phase[i]
+__global__ void row_phase_kernel(const uint32_t *__restrict__ strings, long long dim, int norb,
+                                 PhaseList ph, double2 *__restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < dim;
+       r += (long long)gridDim.x * blockDim.x) {
+    uint32_t s = strings[r];
+    double ar = 1.0, ai = 0.0;
+    for (int i = 0; i < norb; ++i) {
+      if ((s >> i) & 1u) {
+        const double br = ph.re[i], bi = ph.im[i];
+        const double nr = ar * br - ai * bi, ni = ar * bi + ai * br;
+        ar = nr;
+        ai = ni;
+      }
+    }
+    out[r] = make_double2(ar, ai);
+  }
+}
+
+constexpr int kTT = 32;
+__global__ void transpose_kernel(const double2 *__restrict__ in, double2 *__restrict__ out,
+                                 long long n_rows, long long n_cols, long long ld_in,
+                                 long long ld_out, long long tiles_c) {
+  __shared__ double2 t[kTT][kTT + 1];
+  for (long long tileid = blockIdx.x;; tileid += gridDim.x) {
+    const long long tr = tileid / tiles_c, tc = tileid - tr * tiles_c;
+    if (tr * kTT >= n_rows) break;
+    const long long r0 = tr * kTT, c0 = tc * kTT;
+    for (int i = threadIdx.y; i < kTT; i += blockDim.y) {
+      const long long r = r0 + i, c = c0 + threadIdx.x;
+      if (r < n_rows && c < n_cols) t[i][threadIdx.x] = in[r * ld_in + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < kTT; i += blockDim.y) {
+      const long long c = c0 + i, r = r0 + threadIdx.x;
+      if (r < n_rows && c < n_cols) out[c * ld_out + r] = t[threadIdx.x][i];
+    }
+    __syncthreads();
+  }
+}
+
+static int grid_for(long long total, int threads, int sm_count) {
+  long long blocks = (total + threads - 1) / threads;
+  long long cap = (long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+cudaError_t launch_givens_single(void *vec, long long ld, long long dim_b, double c, double sr,
+                                 double si, const unsigned long long *s1,
+                                 const unsigned long long *s2, long long n_pairs, int sm_count,
+                                 cudaStream_t stream) {
+  if (n_pairs <= 0 || dim_b <= 0) return cudaSuccess;
+  givens_single_kernel<<<grid_for(n_pairs * dim_b, 256, sm_count), 256, 0, stream>>>(
+      (double2 *)vec, ld, dim_b, c, sr, si, s1, s2, n_pairs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_phase_shift(void *vec, long long ld, long long dim_b, double pr, double pi,
+                               const unsigned long long *indices, long long n, int sm_count,
+                               cudaStream_t stream) {
+  if (n <= 0 || dim_b <= 0) return cudaSuccess;
+  phase_shift_kernel<<<grid_for(n * dim_b, 256, sm_count), 256, 0, stream>>>(
+      (double2 *)vec, ld, dim_b, pr, pi, indices, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_scale(void *vec, long long n_rows, long long n_cols, long long row_stride,
+                             long long col_stride, const void *phase, int sm_count,
+                             cudaStream_t stream) {
+  if (n_rows <= 0 || n_cols <= 0) return cudaSuccess;
+  row_scale_kernel<<<grid_for(n_rows * n_cols, 256, sm_count), 256, 0, stream>>>(
+      (double2 *)vec, n_rows, n_cols, row_stride, col_stride, (const double2 *)phase);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_phase(const uint32_t *strings, long long dim, int norb, const PhaseList &ph,
+                             void *out, int sm_count, cudaStream_t stream) {
+  if (dim <= 0) return cudaSuccess;
+  row_phase_kernel<<<grid_for(dim, 256, sm_count), 256, 0, stream>>>(strings, dim, norb, ph,
+                                                                     (double2 *)out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose(const void *in, void *out, long long n_rows, long long n_cols,
+                             long long ld_in, long long ld_out, int sm_count, cudaStream_t stream) {
+  if (n_rows <= 0 || n_cols <= 0) return cudaSuccess;
+  const long long tiles_r = (n_rows + kTT - 1) / kTT, tiles_c = (n_cols + kTT - 1) / kTT;
+  long long grid = tiles_r * tiles_c;
+  const long long cap = (long long)sm_count * 16;
+  if (grid > cap) grid = cap;
+  transpose_kernel<<<(int)grid, dim3(kTT, 8), 0, stream>>>((const double2 *)in, (double2 *)out,
+                                                           n_rows, n_cols, ld_in, ld_out, tiles_c);
+  return cudaGetLastError();
+}
+
+}  // namespace ffb

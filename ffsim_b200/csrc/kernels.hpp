@@ -1,0 +1,46 @@
+// Launch wrappers of the CUDA kernels (implemented in the .cu files).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_structs.h"
+
+namespace ffb {
+
+struct PhaseList {  // per-orbital phases passed by value
+  double re[32], im[32];
+};
+
+size_t fused_pass_smem_overhead();
+cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t tile_bytes,
+                              cudaStream_t stream);
+cudaError_t launch_givens_single(void *vec, long long ld, long long dim_b, double c, double sr,
+                                 double si, const unsigned long long *s1,
+                                 const unsigned long long *s2, long long n_pairs, int sm_count,
+                                 cudaStream_t stream);
+cudaError_t launch_phase_shift(void *vec, long long ld, long long dim_b, double pr, double pi,
+                               const unsigned long long *indices, long long n, int sm_count,
+                               cudaStream_t stream);
+cudaError_t launch_row_scale(void *vec, long long n_rows, long long n_cols, long long row_stride,
+                             long long col_stride, const void *phase, int sm_count,
+                             cudaStream_t stream);
+cudaError_t launch_row_phase(const uint32_t *strings, long long dim, int norb, const PhaseList &ph,
+                             void *out, int sm_count, cudaStream_t stream);
+cudaError_t launch_transpose(const void *in, void *out, long long n_rows, long long n_cols,
+                             long long ld_in, long long ld_out, int sm_count, cudaStream_t stream);
+
+}  // namespace ffb
+
+namespace ffb {
+cudaError_t launch_side_factor(bool contract, const uint32_t *strings, long long dim, int norb,
+                               const void *mat, int zrep, void *out, int sm_count,
+                               cudaStream_t stream);
+cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t *strings_b,
+                        const void *rowfac, const void *colfac, const void *mab, const void *vec,
+                        void *out, long long row0, long long n_rows, long long dim_b, int norb,
+                        int zrep, int accumulate, int sm_count, cudaStream_t stream);
+cudaError_t launch_vdot(const void *x, const void *y, long long n, void *partial, int n_partial,
+                        void *result, int sm_count, cudaStream_t stream);
+cudaError_t launch_axpby(double ar, double ai, const void *x, double br, double bi, void *y,
+                         long long n, int sm_count, cudaStream_t stream);
+}  // namespace ffb

@@ -1,0 +1,301 @@
+// Plan builder: turns the adjacent-pair Givens sequence of one spin sector into
+// (1) passes over the state, each confining its rotations to a window of
+// orbitals [lo, lo+W) whose C(W, m) strings fit a shared-memory tile, and
+// (2) sub-passes inside a tile, each confining its rotations to a register
+// block of w <= 6 orbitals.  Rotations on disjoint orbital pairs commute, so the
+// sequence is a dependency DAG; both levels take, greedily, the largest
+// dependency-closed set that fits the window.
+//
+// There is no counterpart in the reference: it performs one sweep per rotation
+// (python/ffsim/gates/orbital_rotation.py:132-135).
+#include <algorithm>
+#include <cassert>
+#include <cstdlib>
+#include <cstring>
+
+#include "device_structs.h"
+#include "host.hpp"
+
+namespace ffb {
+
+namespace {
+PlanOptions g_opt = {/*smem_bytes=*/220 * 1024, /*min_cols=*/3, /*max_cols=*/8,
+                     /*sub_window=*/6,          /*threads=*/512, /*beta_mode=*/0};
+std::mutex g_opt_mu;
+}  // namespace
+
+PlanOptions current_options() {
+  std::lock_guard<std::mutex> lk(g_opt_mu);
+  return g_opt;
+}
+
+int class_offset(int w, int mprime) {
+  int off = 0;
+  for (int j = 1; j < mprime; ++j) off += (int)binom(w, j);
+  return off;
+}
+
+int max_window(int norb, int nocc, const PlanOptions &opt) {
+  int64_t budget_amps = opt.smem_bytes / 16;
+  for (int W = norb; W >= 2; --W) {
+    int mlo = std::max(0, nocc - (norb - W)), mhi = std::min(W, nocc);
+    uint64_t maxR = 0;
+    for (int m = mlo; m <= mhi; ++m) maxR = std::max(maxR, binom(W, m));
+    if (maxR >= 65536) continue;  // block offsets are 16-bit
+    if ((int64_t)maxR * std::max(1, opt.min_cols) <= budget_amps) return W;
+  }
+  return std::min(norb, 2);
+}
+
+// Largest dependency-closed subsequence of `remaining` inside [lo, lo+W).
+static std::vector<int> admit(const std::vector<int> &remaining, const std::vector<int> &q, int lo,
+                              int W, size_t cap) {
+  std::vector<int> out;
+  uint64_t blocked = 0;
+  for (int g : remaining) {
+    uint64_t mask = 3ull << q[g];
+    bool inside = q[g] >= lo && q[g] + 1 < lo + W;
+    if (inside && !(blocked & mask) && out.size() < cap)
+      out.push_back(g);
+    else
+      blocked |= mask;
+  }
+  return out;
+}
+
+static std::vector<int> minus(const std::vector<int> &a, const std::vector<int> &taken) {
+  std::vector<int> out;
+  size_t t = 0;
+  for (int g : a) {
+    if (t < taken.size() && taken[t] == g)
+      ++t;
+    else
+      out.push_back(g);
+  }
+  return out;
+}
+
+SideSchedule build_schedule(int norb, int nocc, const std::vector<int> &q, const PlanOptions &opt) {
+  SideSchedule sched;
+  sched.norb = norb;
+  sched.nocc = nocc;
+  if (q.empty() || norb < 2) return sched;
+  const int W = max_window(norb, nocc, opt);
+  const int w = std::max(2, std::min({opt.sub_window, kMaxSubWindow, W}));
+
+  std::vector<int> remaining(q.size());
+  for (size_t g = 0; g < q.size(); ++g) remaining[g] = (int)g;
+
+  while (!remaining.empty()) {
+    std::vector<int> best;
+    int best_lo = 0;
+    for (int lo = 0; lo + W <= norb; ++lo) {
+      std::vector<int> got = admit(remaining, q, lo, W, kMaxRotPerPass);
+      if (got.size() > best.size()) {
+        best.swap(got);
+        best_lo = lo;
+      }
+    }
+    assert(!best.empty());
+    PassSchedule pass;
+    pass.lo = best_lo;
+    pass.W = W;
+    pass.rot_index = best;
+    remaining = minus(remaining, best);
+
+    // level 2: order the pass's rotations into register-block sub-passes.
+    std::vector<int> qrel(best.size());
+    for (size_t t = 0; t < best.size(); ++t) qrel[t] = q[best[t]] - best_lo;
+    std::vector<int> rem2(best.size());
+    for (size_t t = 0; t < best.size(); ++t) rem2[t] = (int)t;
+    std::vector<int> order;
+    while (!rem2.empty()) {
+      std::vector<int> b2;
+      int b2_q0 = 0;
+      for (int q0 = 0; q0 + w <= W; ++q0) {
+        std::vector<int> got = admit(rem2, qrel, q0, w, 1u << 30);
+        if (got.size() > b2.size()) {
+          b2.swap(got);
+          b2_q0 = q0;
+        }
+      }
+      assert(!b2.empty());
+      SubPass sp;
+      sp.q0 = b2_q0;
+      sp.w = w;
+      sp.rot_begin = (int)order.size();
+      for (int t : b2) order.push_back(best[t]);
+      sp.rot_end = (int)order.size();
+      pass.subs.push_back(sp);
+      rem2 = minus(rem2, b2);
+      if ((int)pass.subs.size() == kMaxSubPerPass && !rem2.empty()) {
+        // out of sub-pass slots: hand the rest back to a later pass
+        std::vector<int> back;
+        for (int t : rem2) back.push_back(best[t]);
+        std::vector<int> merged;
+        std::merge(back.begin(), back.end(), remaining.begin(), remaining.end(),
+                   std::back_inserter(merged));
+        remaining.swap(merged);
+        rem2.clear();
+      }
+    }
+    pass.rot_index = order;
+    sched.passes.push_back(std::move(pass));
+  }
+  return sched;
+}
+
+// sum over the set bits of `pattern` (ascending) of C(shift + pos, first_index + i)
+static uint64_t placed_rank(uint64_t pattern, int shift, int first_index) {
+  uint64_t r = 0;
+  int idx = first_index;
+  while (pattern) {
+    int pos = __builtin_ctzll(pattern);
+    pattern &= pattern - 1;
+    r += binom(shift + pos, idx++);
+  }
+  return r;
+}
+
+PassTablesHost build_pass_tables(int norb, int nocc, const PassSchedule &pass) {
+  PassTablesHost T;
+  T.lo = pass.lo;
+  T.W = pass.W;
+  const int lo = pass.lo, W = pass.W, hi_bits = norb - lo - W;
+  const int n_sub = (int)pass.subs.size();
+
+  // block-offset tables: one per sub-pass, shared by every group
+  T.off.assign((size_t)n_sub * kMaxLow * kOffRow, 0);
+  for (int s = 0; s < n_sub; ++s) {
+    const SubPass &sp = pass.subs[s];
+    for (int lp = 0; lp < kMaxLow && lp <= sp.q0; ++lp) {
+      for (int mp = 1; mp < sp.w; ++mp) {
+        std::vector<uint64_t> pats = strings_of(sp.w, mp);
+        for (size_t t = 0; t < pats.size(); ++t) {
+          uint64_t v = placed_rank(pats[t], sp.q0, lp + 1);
+          T.off[((size_t)s * kMaxLow + lp) * kOffRow + class_offset(sp.w, mp) + t] =
+              (uint16_t)std::min<uint64_t>(v, 65535);
+        }
+      }
+    }
+  }
+
+  int mlo = std::max(0, nocc - (norb - W)), mhi = std::min(W, nocc);
+  for (int m = mlo; m <= mhi; ++m) {
+    PassGroupHost G;
+    G.m = m;
+    G.R = (int)binom(W, m);
+    int outside = nocc - m;  // electrons outside the window
+    G.l_min = std::max(0, outside - hi_bits);
+    int l_max = std::min(lo, outside);
+    G.n_low = l_max - G.l_min + 1;
+    std::vector<uint64_t> pats = strings_of(W, m);
+    G.tabrow.resize((size_t)G.n_low * G.R);
+    for (int l = G.l_min; l <= l_max; ++l)
+      for (int r = 0; r < G.R; ++r)
+        G.tabrow[(size_t)(l - G.l_min) * G.R + r] = (uint32_t)placed_rank(pats[r], lo, l + 1);
+    for (int l = G.l_min; l <= l_max; ++l) {
+      int h = outside - l;
+      std::vector<uint64_t> Hs = strings_of(hi_bits, h), Ls = strings_of(lo, l);
+      for (uint64_t H : Hs) {
+        uint64_t hb = placed_rank(H, lo + W, l + m + 1);
+        for (uint64_t L : Ls) {
+          G.combo_base.push_back((uint32_t)(hb + rank_of(L)));
+          G.combo_low.push_back((uint8_t)(l - G.l_min));
+        }
+      }
+    }
+    // register blocks of every sub-pass
+    G.subs.resize(n_sub);
+    for (int s = 0; s < n_sub; ++s) {
+      const SubPass &sp = pass.subs[s];
+      GroupSubHost &gs = G.subs[s];
+      std::memset(gs.seg_mp, 0, sizeof(gs.seg_mp));
+      std::memset(gs.seg_begin, 0, sizeof(gs.seg_begin));
+      std::memset(gs.seg_count, 0, sizeof(gs.seg_count));
+      int up_bits = W - sp.q0 - sp.w;
+      std::vector<int> classes;
+      for (int mp = 1; mp < sp.w; ++mp) classes.push_back(mp);
+      std::stable_sort(classes.begin(), classes.end(), [&](int a, int b) {
+        return binom(sp.w - 2, a - 1) > binom(sp.w - 2, b - 1);
+      });
+      for (int mp : classes) {
+        int begin = (int)gs.blocks.size();
+        uint64_t n_up = 1ull << up_bits;
+        for (uint64_t Hp = 0; Hp < n_up; ++Hp) {
+          int lp = m - __builtin_popcountll(Hp) - mp;
+          if (lp < 0 || lp > sp.q0) continue;
+          assert(lp < kMaxLow);
+          uint64_t hb = placed_rank(Hp, sp.q0 + sp.w, lp + mp + 1);
+          uint64_t nL = binom(sp.q0, lp);
+          for (uint64_t r = 0; r < nL; ++r) {
+            uint64_t base = hb + r;
+            assert(base < (1u << 24));
+            gs.blocks.push_back((uint32_t)base | ((uint32_t)lp << 24));
+          }
+        }
+        int count = (int)gs.blocks.size() - begin;
+        if (count > 0) {
+          gs.seg_mp[gs.n_seg] = mp;
+          gs.seg_begin[gs.n_seg] = begin;
+          gs.seg_count[gs.n_seg] = count;
+          ++gs.n_seg;
+          G.has_blocks = true;
+        }
+      }
+    }
+    T.groups.push_back(std::move(G));
+  }
+  std::stable_sort(T.groups.begin(), T.groups.end(),
+                   [](const PassGroupHost &a, const PassGroupHost &b) { return a.R > b.R; });
+  return T;
+}
+
+}  // namespace ffb
+
+using namespace ffb;
+
+extern "C" {
+
+int ffb_set_option(const char *key, int64_t value) {
+  if (!key) return fail(FFB_EINVAL, "ffb_set_option: NULL key");
+  std::lock_guard<std::mutex> lk(g_opt_mu);
+  std::string k(key);
+  if (k == "smem_bytes") {
+    if (value < 4096 || value > 227 * 1024) return fail(FFB_EINVAL, "smem_bytes out of range");
+    g_opt.smem_bytes = value;
+  } else if (k == "min_cols") {
+    if (value < 1 || value > 64) return fail(FFB_EINVAL, "min_cols out of range");
+    g_opt.min_cols = (int)value;
+  } else if (k == "max_cols") {
+    if (value < 1 || value > 256) return fail(FFB_EINVAL, "max_cols out of range");
+    g_opt.max_cols = (int)value;
+  } else if (k == "sub_window") {
+    if (value < 2 || value > kMaxSubWindow) return fail(FFB_EINVAL, "sub_window out of range");
+    g_opt.sub_window = (int)value;
+  } else if (k == "threads") {
+    if (value < 32 || value > 1024 || value % 32) return fail(FFB_EINVAL, "threads out of range");
+    g_opt.threads = (int)value;
+  } else if (k == "beta_mode") {
+    if (value < 0 || value > 2) return fail(FFB_EINVAL, "beta_mode out of range");
+    g_opt.beta_mode = (int)value;
+  } else {
+    return fail(FFB_EINVAL, "ffb_set_option: unknown key " + k);
+  }
+  return FFB_OK;
+}
+
+int64_t ffb_get_option(const char *key) {
+  if (!key) return -1;
+  std::lock_guard<std::mutex> lk(g_opt_mu);
+  std::string k(key);
+  if (k == "smem_bytes") return g_opt.smem_bytes;
+  if (k == "min_cols") return g_opt.min_cols;
+  if (k == "max_cols") return g_opt.max_cols;
+  if (k == "sub_window") return g_opt.sub_window;
+  if (k == "threads") return g_opt.threads;
+  if (k == "beta_mode") return g_opt.beta_mode;
+  return -1;
+}
+
+}  // extern "C"

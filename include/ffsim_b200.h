@@ -1,0 +1,196 @@
+/*
+ * ffsim_b200.h -- C ABI of the B200-native determinant-space statevector hot path.
+ *
+ * This is the drop-in boundary for the path SURVEY.md section 8 names.  Every
+ * entry point says which reference interface it replaces; paths are relative to
+ * the reference tree (qiskit-community/ffsim 0.0.85.dev).
+ *
+ * Conventions
+ *   - plain C, no exceptions: every function returns FFB_OK (0) or a negative
+ *     FFB_E* code; ffb_last_error() returns the thread-local message.
+ *   - the state is complex128, row-major (dim_a x dim_b): row = alpha string,
+ *     column = beta string (python/ffsim/states/dimensions.py:18-50).
+ *   - pointers named *_dev are device pointers; everything else is host memory.
+ *     The caller owns every buffer.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = default stream).  Calls are asynchronous with respect to the host.
+ *   - a handle is safe to use from one thread / one stream at a time.
+ *   - there is no CPU fallback: device entry points return FFB_ECUDA when no
+ *     CUDA device is usable.
+ */
+#ifndef FFSIM_B200_H
+#define FFSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB_VERSION 100 /* 0.1.0 */
+
+enum {
+  FFB_OK = 0,
+  FFB_EINVAL = -1, /* bad argument (ValueError / TypeError on the reference side) */
+  FFB_ECUDA = -2,  /* CUDA runtime error, or no device */
+  FFB_ENOMEM = -3,
+  FFB_EINTERNAL = -4
+};
+
+typedef struct ffb_c128 {
+  double re, im;
+} ffb_c128;
+
+/* One Givens rotation as the reference's decomposition returns it: the tuple
+ * (c, s, i, j) of src/linalg/givens.rs:16, |i-j| == 1. */
+typedef struct ffb_givens_rotation {
+  double c;
+  ffb_c128 s;
+  int32_t i, j;
+} ffb_givens_rotation;
+
+typedef struct ffb_tables ffb_tables; /* string tables of one spin sector */
+typedef struct ffb_plan ffb_plan;     /* fused orbital-rotation schedule */
+
+int ffb_version(void);
+const char *ffb_last_error(void);
+/* Number of usable CUDA devices (0 when there is none; never fails). */
+int ffb_device_count(void);
+/* Make `device` current for the calling thread (cudaSetDevice). */
+int ffb_set_device(int device);
+
+/* ------------------------------------------------------------------ tables
+ * Replaces python/ffsim/_cistring.py:21-42 (pyscf.fci.cistring make_strings /
+ * gen_occslst) and the cached address tables of
+ * python/ffsim/gates/orbital_rotation.py:203-236.  Host side is built at
+ * creation; the device copy is made on first use by a device entry point. */
+int ffb_tables_create(int norb, int nocc, ffb_tables **out);
+void ffb_tables_destroy(ffb_tables *t);
+int64_t ffb_tables_dim(const ffb_tables *t);
+int ffb_tables_norb(const ffb_tables *t);
+int ffb_tables_nocc(const ffb_tables *t);
+/* strings: int64[dim], ascending (== cistring.make_strings(range(norb), nocc)). */
+int ffb_tables_strings(const ffb_tables *t, int64_t *out);
+/* occupations: uint64[dim * nocc] row-major (== gen_occslst cast to np.uint). */
+int ffb_tables_occupations(const ffb_tables *t, uint64_t *out);
+/* address of each string (colexicographic rank; pyscf strs2addr). */
+int ffb_tables_strs2addr(const ffb_tables *t, const int64_t *strings, int64_t n, int64_t *out);
+/* _zero_one_subspace_indices(norb, nocc, (i, j)) (orbital_rotation.py:203-213):
+ * writes 2*P addresses, first half = orbital i occupied & j empty, second half
+ * = j occupied & i empty, pair-aligned.  *n_pairs = P = C(norb-2, nocc-1). */
+int64_t ffb_tables_n_pairs(const ffb_tables *t);
+int ffb_tables_zero_one_subspace(const ffb_tables *t, int i, int j, uint64_t *out, int64_t *n_pairs);
+/* _one_subspace_indices(norb, nocc, (i,)) (orbital_rotation.py:216-226). */
+int64_t ffb_tables_n_one(const ffb_tables *t);
+int ffb_tables_one_subspace(const ffb_tables *t, int i, uint64_t *out, int64_t *n);
+
+/* ------------------------------------------------------- host decomposition
+ * Replaces _lib.givens_decomposition (src/linalg/givens.rs:71-149,
+ * python/ffsim/linalg/givens.py:59-156).  mat: row-major n x n.  rots must have
+ * room for n(n-1)/2 entries; phases for n.  Non-square input cannot be
+ * expressed here (the Python wrapper raises ValueError as givens.rs:78-80). */
+int ffb_givens_decomposition(const ffb_c128 *mat, int n, double tol, ffb_givens_rotation *rots,
+                             int *n_rot, ffb_c128 *phases);
+
+/* ------------------------------------------------- _lib-level device kernels
+ * One launch per call, same arithmetic as the Rust kernels.  `ld` is the row
+ * stride of vec in elements (dim_b for a contiguous state). */
+
+/* src/gates/orbital_rotation.rs:20 apply_givens_rotation_in_place */
+int ffb_apply_givens_rotation_in_place(void *vec_dev, int64_t dim_a, int64_t dim_b, int64_t ld,
+                                       double c, ffb_c128 s, const uint64_t *slice1_dev,
+                                       const uint64_t *slice2_dev, int64_t n_pairs, void *stream);
+/* src/gates/phase_shift.rs:18 apply_phase_shift_in_place */
+int ffb_apply_phase_shift_in_place(void *vec_dev, int64_t dim_a, int64_t dim_b, int64_t ld,
+                                   ffb_c128 phase, const uint64_t *indices_dev, int64_t n_indices,
+                                   void *stream);
+
+/* ------------------------------------------------ fused orbital rotation
+ * Replaces the two loops of _apply_orbital_rotation_spinful
+ * (python/ffsim/gates/orbital_rotation.py:117-154): all Givens rotations and
+ * phase shifts of both spin sectors, fused into a few passes over the state.
+ *
+ * rots_x / phases_x are the output of ffb_givens_decomposition for that spin
+ * (n_x < 0 or rots_x == NULL && phases_x == NULL means "leave this spin alone",
+ * the `None` member of the reference's mat tuple).  The plan caches the pass
+ * structure, which depends only on (norb, nocc, orbital pairs); it can be
+ * re-used with new coefficients through ffb_plan_update_coefficients. */
+int ffb_plan_orbital_rotation(ffb_tables *tables_a, ffb_tables *tables_b,
+                              const ffb_givens_rotation *rots_a, int n_a, const ffb_c128 *phases_a,
+                              const ffb_givens_rotation *rots_b, int n_b, const ffb_c128 *phases_b,
+                              ffb_plan **out);
+void ffb_plan_destroy(ffb_plan *p);
+/* Replace the coefficients (c, s, phases) of an existing plan.  The orbital pairs
+ * and the active/inactive state of each spin must be those the plan was built
+ * with, otherwise FFB_EINVAL is returned and the plan is left unchanged. */
+int ffb_plan_update_coefficients(ffb_plan *p, const ffb_givens_rotation *rots_a, int n_a,
+                                 const ffb_c128 *phases_a, const ffb_givens_rotation *rots_b,
+                                 int n_b, const ffb_c128 *phases_b);
+/* Bytes of device workspace ffb_apply_orbital_rotation needs for this plan and
+ * this many locally held alpha rows (0 = none). */
+int64_t ffb_plan_workspace_bytes(const ffb_plan *p, int64_t n_rows_a);
+/* Introspection for tests / DESIGN.md: number of passes per side, and the
+ * number of state passes (read+write sweeps) the whole op performs. */
+int ffb_plan_describe(const ffb_plan *p, char *buf, size_t buflen);
+int ffb_plan_n_state_passes(const ffb_plan *p);
+/* Apply to a contiguous (dim_a x dim_b) state on the device, in place. */
+int ffb_apply_orbital_rotation(ffb_plan *p, void *vec_dev, void *workspace_dev, void *stream);
+/* One spin side only, acting on the ROW index of an arbitrary row-major
+ * (n_rows_total == tables dim) x n_cols matrix with row stride ld: the building
+ * block of the row-sharded multi-GPU path (local columns = any slice of the
+ * other index).  side: 0 = alpha rotations of the plan, 1 = beta rotations. */
+int ffb_apply_orbital_rotation_rows(ffb_plan *p, int side, void *mat_dev, int64_t n_cols, int64_t ld,
+                                    void *stream);
+
+/* ------------------------------------------------------ diagonal operators
+ * Replaces src/gates/diag_coulomb.rs:21,95 (num / z representation),
+ * src/gates/num_op_sum.rs:20, src/contract/diag_coulomb.rs:22,100 and
+ * src/contract/num_op_sum.rs:20.  Matrices are host pointers, row-major
+ * norb x norb; NULL means "all ones" (evolution) / "all zeros" (contraction).
+ * row0 / n_rows select a contiguous block of alpha rows held locally
+ * (row0 = 0, n_rows = dim_a for the whole state); vec_dev points at that block.
+ */
+
+/* vec[a,b] *= aphase(a) * bphase(b) * prod_{i in a, j in b} mat_exp_ab[i][j]
+ * (z representation: conjugate selected by the string bits, all orbitals). */
+int ffb_apply_diag_coulomb_evolution(ffb_tables *tables_a, ffb_tables *tables_b,
+                                     const ffb_c128 *mat_exp_aa, const ffb_c128 *mat_exp_ab,
+                                     const ffb_c128 *mat_exp_bb, int z_representation,
+                                     void *vec_dev, int64_t row0, int64_t n_rows, void *stream);
+/* vec[a,b] *= prod_{i in a} phases_a[i] * prod_{j in b} phases_b[j]; either may be NULL. */
+int ffb_apply_num_op_sum_evolution(ffb_tables *tables_a, ffb_tables *tables_b,
+                                   const ffb_c128 *phases_a, const ffb_c128 *phases_b,
+                                   void *vec_dev, int64_t row0, int64_t n_rows, void *stream);
+/* out[a,b] (+)= coeff(a,b) * vec[a,b]; accumulate != 0 keeps the old out
+ * (the reference's into_buffer form), 0 overwrites (no read of out). */
+int ffb_contract_diag_coulomb(ffb_tables *tables_a, ffb_tables *tables_b, const double *mat_aa,
+                              const double *mat_ab, const double *mat_bb, int z_representation,
+                              const void *vec_dev, void *out_dev, int accumulate, int64_t row0,
+                              int64_t n_rows, void *stream);
+int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const double *coeffs_a,
+                            const double *coeffs_b, const void *vec_dev, void *out_dev,
+                            int accumulate, int64_t row0, int64_t n_rows, void *stream);
+
+/* ---------------------------------------------------------------- utilities */
+/* out[c, r] = in[r, c]; in is n_rows x n_cols with row stride ld_in, out has row stride ld_out. */
+int ffb_transpose(const void *in_dev, void *out_dev, int64_t n_rows, int64_t n_cols, int64_t ld_in,
+                  int64_t ld_out, void *stream);
+/* result_dev[0] = sum conj(x) * y as one complex128 (device scalar, 16 bytes). */
+int ffb_vdot(const void *x_dev, const void *y_dev, int64_t n, void *result_dev, void *stream);
+/* y = alpha * x + beta * y, complex scalars */
+int ffb_axpby(ffb_c128 alpha, const void *x_dev, ffb_c128 beta, void *y_dev, int64_t n, void *stream);
+
+/* Tuning knobs (process-wide; read when a plan is built).  key/value pairs:
+ *   "smem_bytes"   shared-memory budget per tile (default: device opt-in max)
+ *   "min_cols"     smallest column strip per tile (default 4)
+ *   "max_cols"     largest column strip (default 8)
+ *   "sub_window"   register-block width, 2..6 (default 6)
+ *   "threads"      CTA size of the fused pass kernel (default 512)
+ * Unknown keys return FFB_EINVAL. */
+int ffb_set_option(const char *key, int64_t value);
+int64_t ffb_get_option(const char *key);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFSIM_B200_H */

@@ -1,0 +1,118 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into libffsim_b200.so.
+//
+// Host emulation of fused_pass_kernel's index logic: consumes exactly the tables
+// the plan builder uploads to the device (tile row tables, combination bases,
+// register-block lists, block-offset tables, rotation order) and applies the
+// rotations to a host vector the way the kernel does.  It lets the CPU-only test
+// suite validate the schedule and every index table without a GPU; it is not a
+// product path and nothing in ffsim_b200/ can reach it.
+#include <complex>
+#include <cstring>
+#include <vector>
+
+#include "../../ffsim_b200/csrc/host.hpp"
+
+using namespace ffb;
+
+static void zrot(cplx &x, cplx &y, double c, cplx s) {
+  cplx nx = c * x + s * y, ny = c * y - std::conj(s) * x;
+  x = nx;
+  y = ny;
+}
+
+extern "C" int ffb_hostcheck_apply_side(int norb, int nocc, const ffb_givens_rotation *rots, int n_rot,
+                                        const ffb_c128 *phases, void *vec /* dim x n_cols, row-major */,
+                                        int64_t n_cols, int64_t smem_bytes, int min_cols, int sub_window,
+                                        int *n_passes_out, int *n_subs_out) {
+  PlanOptions opt = current_options();
+  if (smem_bytes > 0) opt.smem_bytes = smem_bytes;
+  if (min_cols > 0) opt.min_cols = min_cols;
+  if (sub_window > 0) opt.sub_window = sub_window;
+  cplx *data = reinterpret_cast<cplx *>(vec);
+  std::vector<NormRot> nr;
+  std::vector<int> q;
+  for (int k = 0; k < n_rot; ++k) {
+    nr.push_back(normalise(rots[k]));
+    q.push_back(nr.back().q);
+  }
+  if (nocc == 0 || nocc == norb) q.clear();
+  SideSchedule sched = build_schedule(norb, nocc, q, opt);
+  int64_t dim = (int64_t)binom(norb, nocc);
+  int total_subs = 0;
+  std::vector<char> seen(q.size(), 0);
+  for (const PassSchedule &ps : sched.passes) {
+    PassTablesHost T = build_pass_tables(norb, nocc, ps);
+    total_subs += (int)ps.subs.size();
+    std::vector<char> row_seen(dim, 0);
+    for (const PassGroupHost &G : T.groups) {
+      const int R = G.R;
+      for (size_t combo = 0; combo < G.combo_base.size(); ++combo) {
+        const uint32_t rowbase = G.combo_base[combo];
+        const uint32_t *tab = G.tabrow.data() + (size_t)G.combo_low[combo] * R;
+        for (int r = 0; r < R; ++r) {
+          int64_t row = (int64_t)rowbase + tab[r];
+          if (row < 0 || row >= dim || row_seen[row]) return -100;  // tiles must partition the rows
+          row_seen[row] = 1;
+        }
+        for (int64_t col = 0; col < n_cols; ++col) {
+          std::vector<cplx> tile(R);
+          for (int r = 0; r < R; ++r) tile[r] = data[((int64_t)rowbase + tab[r]) * n_cols + col];
+          for (size_t s = 0; s < ps.subs.size(); ++s) {
+            const SubPass &sp = ps.subs[s];
+            const GroupSubHost &gs = G.subs[s];
+            const uint16_t *offtab = T.off.data() + s * kMaxLow * kOffRow;
+            std::vector<char> used(R, 0);
+            for (int sg = 0; sg < gs.n_seg; ++sg) {
+              const int mp = gs.seg_mp[sg];
+              std::vector<uint64_t> pats = strings_of(sp.w, mp);
+              for (int b = 0; b < gs.seg_count[sg]; ++b) {
+                uint32_t entry = gs.blocks[gs.seg_begin[sg] + b];
+                int base = entry & 0xFFFFFF;
+                const uint16_t *o = offtab + (entry >> 24) * kOffRow + class_offset(sp.w, mp);
+                std::vector<int> idx(pats.size());
+                for (size_t t = 0; t < pats.size(); ++t) {
+                  idx[t] = base + o[t];
+                  if (idx[t] < 0 || idx[t] >= R || used[idx[t]]) return -101;  // blocks are disjoint
+                  used[idx[t]] = 1;
+                }
+                for (int rr = sp.rot_begin; rr < sp.rot_end; ++rr) {
+                  const NormRot &g = nr[ps.rot_index[rr]];
+                  int qq = g.q - ps.lo - sp.q0;
+                  if (qq < 0 || qq + 1 >= sp.w) return -102;
+                  for (size_t t = 0; t < pats.size(); ++t) {
+                    uint64_t S = pats[t];
+                    if (((S >> qq) & 3) == 1) {
+                      uint64_t S2 = S ^ (3ull << qq);
+                      zrot(tile[idx[rank_of(S)]], tile[idx[rank_of(S2)]], g.c, g.s);
+                    }
+                  }
+                }
+              }
+            }
+          }
+          for (int r = 0; r < R; ++r) data[((int64_t)rowbase + tab[r]) * n_cols + col] = tile[r];
+        }
+      }
+    }
+    for (int64_t r = 0; r < dim; ++r)
+      if (!row_seen[r]) return -103;
+    for (int g : ps.rot_index) {
+      if (seen[g]) return -104;
+      seen[g] = 1;
+    }
+  }
+  for (size_t g = 0; g < q.size(); ++g)
+    if (!seen[g]) return -105;
+  if (phases) {
+    std::vector<uint64_t> strs = strings_of(norb, nocc);
+    for (int64_t r = 0; r < dim; ++r) {
+      cplx f(1.0, 0.0);
+      for (int i = 0; i < norb; ++i)
+        if ((strs[r] >> i) & 1) f *= cplx(phases[i].re, phases[i].im);
+      for (int64_t col = 0; col < n_cols; ++col) data[r * n_cols + col] *= f;
+    }
+  }
+  if (n_passes_out) *n_passes_out = (int)sched.passes.size();
+  if (n_subs_out) *n_subs_out = total_subs;
+  return 0;
+}

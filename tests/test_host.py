@@ -1,0 +1,186 @@
+"""CPU-only tests: C ABI surface, bit-exact tables, host decomposition, plan tables."""
+
+import ctypes
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from ffsim_b200 import _lib as L
+from ffsim_b200 import cistring as fcis
+from ffsim_b200.linalg import givens_decomposition
+from oracle import cistring, cref, gates, givens, models, rand
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOSTCHECK = os.path.join(ROOT, "tests", "hostcheck", "libffsim_b200_hostcheck.so")
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ffsim_b200.h")).read()
+    declared = set(re.findall(r"\b(ffb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L.lib, name), f"{name} is declared in the header but not exported"
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    assert L.lib.ffb_version() == 100
+
+
+def test_no_device_is_reported_not_faked():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    assert L.lib.ffb_device_count() == 0
+    import ffsim_b200
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ffsim_b200.apply_orbital_rotation(np.ones(1, complex), np.eye(1), 1, (1, 1))
+
+
+def test_package_does_not_import_oracle():
+    out = subprocess.run(
+        ["grep", "-rlE", r"^\s*(from|import)\s+oracle", os.path.join(ROOT, "ffsim_b200")],
+        capture_output=True, text=True)
+    assert out.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("norb", range(0, 10))
+def test_tables_bit_exact(norb):
+    for k in range(0, norb + 1):
+        s = fcis.make_strings(norb, k)
+        assert s.dtype == np.int64 and np.array_equal(s, cistring.make_strings(range(norb), k))
+        occ = fcis.gen_occslst(norb, k)
+        assert occ.dtype == np.uint64 and np.array_equal(occ, cistring.gen_occslst(range(norb), k))
+        assert np.array_equal(fcis.strs2addr(norb, k, s), np.arange(len(s)))
+        for i in range(norb):
+            if k >= 1:
+                assert np.array_equal(fcis.one_subspace_indices(norb, k, (i,)),
+                                      cistring.one_subspace_indices(norb, k, (i,)))
+            for j in range(norb):
+                if i != j:
+                    assert np.array_equal(fcis.zero_one_subspace_indices(norb, k, (i, j)),
+                                          cistring.zero_one_subspace_indices(norb, k, (i, j)))
+
+
+def test_tables_large_sector_matches_oracle():
+    for norb, k in [(16, 5), (18, 7), (20, 3)]:
+        assert np.array_equal(fcis.make_strings(norb, k), cistring.make_strings(range(norb), k))
+        assert np.array_equal(fcis.zero_one_subspace_indices(norb, k, (7, 8)),
+                              cistring.zero_one_subspace_indices(norb, k, (7, 8)))
+
+
+def test_tables_errors():
+    h = ctypes.c_void_p()
+    assert L.lib.ffb_tables_create(3, 4, ctypes.byref(h)) == L.FFB_EINVAL
+    assert "nocc" in L.last_error()
+    assert L.lib.ffb_tables_create(-1, 0, ctypes.byref(h)) == L.FFB_EINVAL
+    with pytest.raises(ValueError):
+        fcis.strs2addr(4, 2, [0b0111])
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 8, 12, 16, 20, 24])
+def test_givens_decomposition_matches_oracle(n):
+    u = rand.random_unitary(n, seed=100 + n) if n else np.zeros((0, 0), complex)
+    rots, phases = givens_decomposition(u)
+    want_rots, want_phases = givens.givens_decomposition(u)
+    assert [(r.i, r.j) for r in rots] == [(i, j) for _, _, i, j in want_rots]
+    for r, (c, s, _, _) in zip(rots, want_rots):
+        assert abs(r.c - c) < 1e-12 and abs(r.s - s) < 1e-12
+    np.testing.assert_allclose(phases, want_phases, atol=1e-12)
+
+
+def test_givens_decomposition_edge_cases():
+    rots, phases = givens_decomposition(np.eye(5))  # tests/python/linalg/givens_test.py:122-128
+    assert rots == [] and np.allclose(phases, 1)
+    with pytest.raises(ValueError):
+        givens_decomposition(np.zeros((2, 3)))
+    u = np.load(os.path.join(ROOT, "tests", "golden", "orbital_rotation-0.npy"))
+    rots, phases = givens_decomposition(u)
+    want_rots, _ = givens.givens_decomposition(u)
+    assert len(rots) == len(want_rots) < 28  # exact zeros give fewer rotations
+    perm = np.eye(4)[[1, 0, 3, 2]]
+    rots, phases = givens_decomposition(perm)
+    want_rots, want_phases = givens.givens_decomposition(perm)
+    assert [(r.c, r.s, r.i, r.j) for r in rots] == [tuple(w) for w in want_rots]
+
+
+# ---------------------------------------------------------------- plan tables via the host emulator
+
+def _hostcheck():
+    if not os.path.exists(HOSTCHECK):
+        subprocess.run(["make", "-C", os.path.dirname(HOSTCHECK)], check=True)
+    hc = ctypes.CDLL(HOSTCHECK)
+    hc.ffb_hostcheck_apply_side.restype = ctypes.c_int
+    hc.ffb_hostcheck_apply_side.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    return hc
+
+
+def _emulate(norb, k, n_cols, smem, min_cols, sub_window, seed, u=None):
+    from ffsim_b200.linalg.givens import _decompose_raw
+
+    hc = _hostcheck()
+    rng = np.random.default_rng(seed)
+    dim = math.comb(norb, k)
+    if u is None:
+        u = rand.random_unitary(norb, seed=rng)
+    vec = rand.random_state_vector(dim * n_cols, seed=rng).reshape(dim, n_cols)
+    rots, ph = _decompose_raw(u)
+    rots = np.ascontiguousarray(rots)
+    got = np.ascontiguousarray(vec.copy())
+    n_pass, n_sub = ctypes.c_int(), ctypes.c_int()
+    rc = hc.ffb_hostcheck_apply_side(norb, k, L.ptr(rots), len(rots), L.ptr(ph), L.ptr(got), n_cols, smem,
+                                     min_cols, sub_window, ctypes.byref(n_pass), ctypes.byref(n_sub))
+    assert rc == 0, f"hostcheck invariant {rc} failed for norb={norb} k={k}"
+    want = vec.copy()
+    gates._rotate_one_spin(want, givens.givens_decomposition(u), norb, k)
+    err = np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-300)
+    return err, n_pass.value, n_sub.value
+
+
+@pytest.mark.parametrize("norb", range(1, 9))
+def test_plan_tables_all_small_sectors(norb):
+    for k in range(0, norb + 1):
+        for smem, mc, sw in [(220 * 1024, 3, 6), (2048, 4, 3), (1024, 2, 2), (4096, 1, 4), (8192, 4, 5)]:
+            err, _, _ = _emulate(norb, k, 3, smem, mc, sw, seed=norb * 100 + k)
+            assert err < 1e-13, (norb, k, smem, mc, sw, err)
+
+
+@pytest.mark.parametrize("norb,k,smem,max_passes", [
+    (12, 6, 220 * 1024, 1), (12, 6, 16 * 1024, 4), (14, 5, 32 * 1024, 4), (16, 5, 220 * 1024, 1),
+    (16, 8, 220 * 1024, 4)])
+def test_plan_tables_baseline_shapes(norb, k, smem, max_passes):
+    err, n_pass, n_sub = _emulate(norb, k, 1, smem, 3, 6, seed=7)
+    assert err < 1e-13
+    assert 1 <= n_pass <= max_passes
+    assert n_sub <= norb * (norb - 1) // 2
+
+
+def test_plan_tables_sparse_unitary():
+    u = np.load(os.path.join(ROOT, "tests", "golden", "orbital_rotation-0.npy"))
+    err, _, _ = _emulate(8, 5, 2, 4096, 2, 4, seed=3, u=u)
+    assert err < 1e-13
+    err, _, _ = _emulate(6, 3, 2, 220 * 1024, 3, 6, seed=3, u=np.eye(6))
+    assert err < 1e-15
+
+
+# ---------------------------------------------------------------- the C restatement used as CPU baseline
+
+@pytest.mark.parametrize("norb,nelec", [(5, (3, 2)), (8, (4, 3)), (6, (0, 3)), (4, (4, 2)), (7, (2, 5))])
+def test_c_restatement_matches_numpy_oracle(norb, nelec):
+    rng = np.random.default_rng(norb)
+    v = rand.random_state_vector(models.dim(norb, nelec), seed=rng)
+    u = rand.random_unitary(norb, seed=rng)
+    np.testing.assert_allclose(cref.apply_orbital_rotation(v, u, norb, nelec),
+                               gates.apply_orbital_rotation(v, u, norb, nelec), atol=1e-13)
+    mats = (rand.random_real_symmetric_matrix(norb, seed=rng), rng.standard_normal((norb, norb)),
+            rand.random_real_symmetric_matrix(norb, seed=rng))
+    for z in (False, True):
+        np.testing.assert_allclose(
+            cref.apply_diag_coulomb_evolution(v, mats, 0.3, norb, nelec, z_representation=z),
+            gates.apply_diag_coulomb_evolution(v, mats, 0.3, norb, nelec, z_representation=z), atol=1e-13)
