@@ -60,17 +60,46 @@ def to_device(vec: Any, *, copy: bool) -> tuple[torch.Tensor, Kind]:
                 elif copy or not t.is_contiguous():
                     t = t.clone(memory_format=torch.contiguous_format)
             return t, Kind(device=vec.device)
-        t = vec.reshape(-1).to(torch.complex128).contiguous()
-        return t.cuda(non_blocking=False), Kind(torch_cpu=True)
+        t = vec.detach().reshape(-1).to(torch.complex128).contiguous()
+        return _upload(t.numpy()), Kind(torch_cpu=True)
     arr = np.ascontiguousarray(np.asarray(vec).reshape(-1), dtype=np.complex128)
-    return torch.from_numpy(arr).cuda(), Kind(numpy=True)
+    return _upload(arr), Kind(numpy=True)
+
+
+_STAGE_MIN_BYTES = 1 << 20
+
+
+def _upload(arr: np.ndarray) -> torch.Tensor:
+    """Host -> device.  Pinned buffers go straight to the DMA engine; large pageable
+    ones are staged through a pinned buffer from torch's caching host allocator."""
+    if not arr.flags.writeable:
+        arr = arr.copy()
+    src = torch.from_numpy(arr)
+    if arr.nbytes >= _STAGE_MIN_BYTES and not src.is_pinned():
+        stage = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        stage.copy_(src)
+        src = stage
+    out = torch.empty(src.shape, dtype=src.dtype, device="cuda")
+    out.copy_(src, non_blocking=True)
+    torch.cuda.current_stream().synchronize()  # the staging buffer may be recycled after this
+    return out
+
+
+def _download(t: torch.Tensor) -> torch.Tensor:
+    """Device -> host into pinned memory (cached by torch's host allocator)."""
+    if t.numel() * t.element_size() >= _STAGE_MIN_BYTES:
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
+    return t.cpu()
 
 
 def from_device(t: torch.Tensor, kind: Kind):
     if kind.numpy:
-        return t.cpu().numpy()
+        return _download(t).numpy()
     if kind.torch_cpu:
-        return t.cpu()
+        return _download(t)
     return t
 
 

@@ -92,6 +92,8 @@ EXPORTS = {
     "ffb_transpose": (c_int, _P, _P, c_int64, c_int64, c_int64, c_int64, _P),
     "ffb_vdot": (c_int, _P, _P, c_int64, _P, _P),
     "ffb_axpby": (c_int, C128, _P, C128, _P, c_int64, _P),
+    "ffb_profile_begin": (c_int,),
+    "ffb_profile_end": (c_int, c_char_p, c_size_t),
     "ffb_set_option": (c_int, c_char_p, c_int64),
     "ffb_get_option": (c_int64, c_char_p),
 }
@@ -128,6 +130,18 @@ def ptr(arr: np.ndarray | None):
 def c128(z: complex) -> C128:
     z = complex(z)
     return C128(z.real, z.imag)
+
+
+def profile_begin() -> None:
+    check(lib.ffb_profile_begin())
+
+
+def profile_end() -> dict:
+    import json
+
+    buf = ctypes.create_string_buffer(4096)
+    check(lib.ffb_profile_end(buf, len(buf)))
+    return json.loads(buf.value.decode())
 
 
 def set_option(key: str, value: int) -> None:

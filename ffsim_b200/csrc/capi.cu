@@ -25,6 +25,47 @@ static_assert(ffb::kMaxLow == ffb::kMaxLowDev, "kMaxLow mismatch");
 
 namespace {
 
+// ---- optional launch profiling (bench.py): CUDA events around the hot kernels,
+// recorded on the stream they are launched on.
+enum { kProfFused = 0, kProfDiag = 1, kProfTranspose = 2, kProfOther = 3, kProfKinds = 4 };
+const char *const kProfNames[kProfKinds] = {"fused_pass_kernel", "diag_kernel", "transpose_kernel", "other"};
+struct ProfState {
+  bool enabled = false;
+  std::mutex mu;
+  struct Rec {
+    cudaEvent_t a, b;
+    int kind;
+    double bytes;
+  };
+  std::vector<Rec> recs;
+  long long launches[kProfKinds] = {0, 0, 0, 0};
+};
+ProfState g_prof;
+
+struct ProfScope {
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind;
+  double bytes;
+  bool on;
+  ProfScope(int kind_, double bytes_, cudaStream_t st_) : st(st_), kind(kind_), bytes(bytes_) {
+    g_prof.launches[kind] += 1;
+    on = g_prof.enabled && kind != kProfOther;
+    if (on) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, st);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(b, st);
+      std::lock_guard<std::mutex> lk(g_prof.mu);
+      g_prof.recs.push_back({a, b, kind, bytes});
+    }
+  }
+};
+
 struct DeviceInfo {
   int device = -1;
   int sm_count = 0;
@@ -245,15 +286,18 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
   if (!sp.active || n_cols <= 0 || sp.tables->dim <= 0) return FFB_OK;
   const int64_t dim = sp.tables->dim;
   if (sp.has_phases && !sp.rowphase_ready) {
+    ProfScope prof(kProfOther, 0.0, stream);
     FFB_CUDA(launch_row_phase(sp.tables->d_strings, dim, sp.tables->norb, sp.phases, sp.d_rowphase,
                               plan->dev.sm_count, stream));
     sp.rowphase_ready = true;
   }
   const size_t n_pass = sp.structure ? sp.structure->passes.size() : 0;
   if (n_pass == 0) {
-    if (sp.has_phases)
+    if (sp.has_phases) {
+      ProfScope prof(kProfOther, 0.0, stream);
       FFB_CUDA(launch_row_scale(data, dim, n_cols, row_stride, col_stride, sp.d_rowphase,
                                 plan->dev.sm_count, stream));
+    }
     return FFB_OK;
   }
   const size_t overhead = fused_pass_smem_overhead();
@@ -311,6 +355,8 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
       GroupLaunch &L = P.g[ng++];
       L.R = G.R;
       L.cols = (int)cols;
+      L.inv_cols = 0xFFFFFFFFu / (unsigned)cols + 1u;
+      L.inv_R = 0xFFFFFFFFu / (unsigned)G.R + 1u;
       L.n_combos = (int)G.combo_base.size();
       L.has_blocks = G.has_blocks ? 1 : 0;
       L.tabrow_off = dp.goff[gi].tabrow_off;
@@ -330,7 +376,10 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     size_t per_cta = tile_bytes + overhead + 1024;
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, plan->dev.smem_optin / per_cta));
     grid = (int)std::min<long long>(units, (long long)plan->dev.sm_count * ctas_per_sm);
-    FFB_CUDA(launch_fused_pass(P, grid, plan->opt.threads, tile_bytes, stream));
+    {
+      ProfScope prof(kProfFused, 32.0 * (double)dim * (double)n_cols, stream);
+      FFB_CUDA(launch_fused_pass(P, grid, plan->opt.threads, tile_bytes, stream));
+    }
   }
   return FFB_OK;
 }
@@ -506,11 +555,18 @@ int ffb_apply_orbital_rotation(ffb_plan *p, void *vec_dev, void *workspace_dev, 
   if (!p->side[1].active) return FFB_OK;
   if (!p->beta_transposed) return apply_side(p, 1, vec_dev, p->dim_a, 1, p->dim_b, st);
   if (!workspace_dev) return fail(FFB_EINVAL, "ffb_apply_orbital_rotation: this plan needs a workspace");
-  FFB_CUDA(launch_transpose(vec_dev, workspace_dev, p->dim_a, p->dim_b, p->dim_b, p->dim_a,
-                            p->dev.sm_count, st));
+  const double tbytes = 32.0 * (double)p->dim_a * (double)p->dim_b;
+  {
+    ProfScope prof(kProfTranspose, tbytes, st);
+    FFB_CUDA(launch_transpose(vec_dev, workspace_dev, p->dim_a, p->dim_b, p->dim_b, p->dim_a,
+                              p->dev.sm_count, st));
+  }
   if ((rc = apply_side(p, 1, workspace_dev, p->dim_a, p->dim_a, 1, st)) != FFB_OK) return rc;
-  FFB_CUDA(launch_transpose(workspace_dev, vec_dev, p->dim_b, p->dim_a, p->dim_a, p->dim_b,
-                            p->dev.sm_count, st));
+  {
+    ProfScope prof(kProfTranspose, tbytes, st);
+    FFB_CUDA(launch_transpose(workspace_dev, vec_dev, p->dim_b, p->dim_a, p->dim_a, p->dim_b,
+                              p->dev.sm_count, st));
+  }
   return FFB_OK;
 }
 
@@ -600,6 +656,7 @@ int diag_op(bool contract, ffb_tables *ta, ffb_tables *tb, const void *m_aa, con
     if ((rc = scratch(ta, kSlotMat, mat_bytes, &d_m)) != FFB_OK) return rc;
     if ((rc = scratch(ta, kSlotFactor, (size_t)ta->dim * elem, &fa)) != FFB_OK) return rc;
     FFB_CUDA(cudaMemcpyAsync(d_m, m_aa, (size_t)norb * norb * elem, cudaMemcpyHostToDevice, st));
+    ProfScope prof(kProfOther, 0.0, st);
     FFB_CUDA(launch_side_factor(contract, ta->d_strings, ta->dim, norb, d_m, zrep, fa, di.sm_count, st));
   }
   if (m_bb) {
@@ -609,14 +666,19 @@ int diag_op(bool contract, ffb_tables *ta, ffb_tables *tb, const void *m_aa, con
     if ((rc = scratch(tb, kSlotMat + off, mat_bytes, &d_m)) != FFB_OK) return rc;
     if ((rc = scratch(tb, kSlotFactor + off, (size_t)tb->dim * elem, &fb)) != FFB_OK) return rc;
     FFB_CUDA(cudaMemcpyAsync(d_m, m_bb, (size_t)norb * norb * elem, cudaMemcpyHostToDevice, st));
+    ProfScope prof(kProfOther, 0.0, st);
     FFB_CUDA(launch_side_factor(contract, tb->d_strings, tb->dim, norb, d_m, zrep, fb, di.sm_count, st));
   }
   if (m_ab) {
     if ((rc = scratch(ta, kSlotMatAB, mat_bytes, &d_ab)) != FFB_OK) return rc;
     FFB_CUDA(cudaMemcpyAsync(d_ab, m_ab, (size_t)norb * norb * elem, cudaMemcpyHostToDevice, st));
   }
-  FFB_CUDA(launch_diag(contract, ta->d_strings, tb->d_strings, fa, fb, d_ab, vec, out, row0, n_rows,
-                       tb->dim, norb, zrep, accumulate, di.sm_count, st));
+  {
+    const double amps = (double)n_rows * (double)tb->dim;
+    ProfScope prof(kProfDiag, (contract && accumulate ? 48.0 : 32.0) * amps, st);
+    FFB_CUDA(launch_diag(contract, ta->d_strings, tb->d_strings, fa, fb, d_ab, vec, out, row0, n_rows,
+                         tb->dim, norb, zrep, accumulate, di.sm_count, st));
+  }
   return FFB_OK;
 }
 
@@ -690,6 +752,48 @@ int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const do
                  (cudaStream_t)stream);
 }
 
+int ffb_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  for (auto &r : g_prof.recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.recs.clear();
+  for (int k = 0; k < kProfKinds; ++k) g_prof.launches[k] = 0;
+  g_prof.enabled = true;
+  return FFB_OK;
+}
+
+int ffb_profile_end(char *buf, size_t buflen) {
+  if (!buf || buflen == 0) return fail(FFB_EINVAL, "ffb_profile_end: NULL buffer");
+  FFB_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.enabled = false;
+  double ms[kProfKinds] = {0, 0, 0, 0}, bytes[kProfKinds] = {0, 0, 0, 0};
+  long long timed[kProfKinds] = {0, 0, 0, 0};
+  for (auto &r : g_prof.recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ms[r.kind] += t;
+      bytes[r.kind] += r.bytes;
+      timed[r.kind] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.recs.clear();
+  std::ostringstream os;
+  os.precision(10);
+  os << "{";
+  for (int k = 0; k < kProfKinds; ++k) {
+    os << (k ? ", " : "") << "\"" << kProfNames[k] << "\": {\"launches\": " << g_prof.launches[k]
+       << ", \"timed\": " << timed[k] << ", \"ms\": " << ms[k] << ", \"bytes\": " << bytes[k] << "}";
+  }
+  os << "}";
+  std::snprintf(buf, buflen, "%s", os.str().c_str());
+  return FFB_OK;
+}
+
 int ffb_transpose(const void *in_dev, void *out_dev, int64_t n_rows, int64_t n_cols, int64_t ld_in,
                   int64_t ld_out, void *stream) {
   if (n_rows == 0 || n_cols == 0) return FFB_OK;
@@ -728,6 +832,7 @@ int ffb_axpby(ffb_c128 alpha, const void *x_dev, ffb_c128 beta, void *y_dev, int
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc != FFB_OK) return rc;
+  ProfScope prof(kProfOther, 0.0, (cudaStream_t)stream);
   FFB_CUDA(launch_axpby(alpha.re, alpha.im, x_dev, beta.re, beta.im, y_dev, n, di.sm_count,
                         (cudaStream_t)stream));
   return FFB_OK;

@@ -6,7 +6,7 @@ namespace ffb {
 
 constexpr int kMaxGroups = 33;       // distinct electron counts inside a window
 constexpr int kMaxRotPerPass = 512;  // >= 32*31/2
-constexpr int kMaxSubPerPass = 200;
+constexpr int kMaxSubPerPass = 96;
 constexpr int kMaxLowDev = 16;       // distinct electron counts below a register block
 constexpr int kOffRow = 64;          // u16 entries per row of the block-offset table (2^6 - 2 used)
 constexpr int kMaxSeg = 5;           // classes m' = 1..w-1 of a 6-wide register block
@@ -27,6 +27,8 @@ struct GroupLaunch {
   int cols;                 // tile columns (chosen at launch)
   int n_combos;
   int has_blocks;
+  unsigned inv_cols;        // 0xFFFFFFFF / cols + 1
+  unsigned inv_R;           // 0xFFFFFFFF / R + 1
   uint32_t tabrow_off;      // u32 [n_low][R]
   uint32_t combo_base_off;  // u32 [n_combos]
   uint32_t combo_low_off;   // u8  [n_combos]

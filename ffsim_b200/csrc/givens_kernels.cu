@@ -119,18 +119,28 @@ __device__ __forceinline__ void process_dispatch(int mp, double2 *tile, int cols
 }
 
 constexpr int kOffTabEntries = kMaxLowDev * kOffRow;  // u16 entries of one sub-pass table
+// shared-memory prefix: two block-offset tables + the group's per-sub-pass block lists
+constexpr size_t kFusedSmemOverhead =
+    ((2 * kOffTabEntries * sizeof(uint16_t) + kMaxSubPerPass * sizeof(GroupSubDev)) + 15) / 16 * 16;
+
+// n / d for n * d < 2^32 with a precomputed inv = 0xFFFFFFFF / d + 1 (which wraps to 0 for d == 1)
+__device__ __forceinline__ int fast_div(int n, unsigned inv) {
+  return inv ? (int)__umulhi((unsigned)n, inv) : n;
+}
 
 template <int W>
 __global__ void __launch_bounds__(512, 1)
     fused_pass_kernel(const __grid_constant__ PassParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint16_t *offbuf = reinterpret_cast<uint16_t *>(smem_raw);  // 2 x kOffTabEntries
-  double2 *tile = reinterpret_cast<double2 *>(smem_raw + 2 * kOffTabEntries * sizeof(uint16_t));
+  GroupSubDev *gsub_s = reinterpret_cast<GroupSubDev *>(smem_raw + 2 * kOffTabEntries * sizeof(uint16_t));
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw + kFusedSmemOverhead);
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
   double2 *__restrict__ data = reinterpret_cast<double2 *>(p.data);
   const double2 *__restrict__ rowphase = reinterpret_cast<const double2 *>(p.rowphase);
+  int cached_group = -1;
 
   for (long long unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
     int gi = 0;
@@ -140,6 +150,7 @@ __global__ void __launch_bounds__(512, 1)
     const long long combo = local / G.n_strips;
     const long long strip = local - combo * G.n_strips;
     const int R = G.R, cols = G.cols;
+    const unsigned inv_cols = G.inv_cols, inv_R = G.inv_R;
     const long long col0 = strip * cols;
     const int ncv = (int)min((long long)cols, p.n_cols - col0);
     const uint32_t rowbase = p.u32[G.combo_base_off + combo];
@@ -150,14 +161,14 @@ __global__ void __launch_bounds__(512, 1)
     // ---- load the tile
     if (p.col_stride == 1) {
       for (int e = tid; e < n_el; e += nthr) {
-        const int r = e / cols, j = e - r * cols;
+        const int r = fast_div(e, inv_cols), j = e - r * cols;
         double2 v = make_double2(0.0, 0.0);
         if (j < ncv) v = data[(long long)(rowbase + tab[r]) * p.row_stride + col0 + j];
         tile[e] = v;
       }
     } else {
       for (int e = tid; e < n_el; e += nthr) {
-        const int j = e / R, r = e - j * R;
+        const int j = fast_div(e, inv_R), r = e - j * R;
         double2 v = make_double2(0.0, 0.0);
         if (j < ncv)
           v = data[(long long)(rowbase + tab[r]) * p.row_stride + (col0 + j) * p.col_stride];
@@ -167,6 +178,12 @@ __global__ void __launch_bounds__(512, 1)
     if (G.has_blocks && p.n_sub > 0) {
       for (int e = tid; e < kOffTabEntries / 2; e += nthr)
         reinterpret_cast<uint32_t *>(offbuf)[e] = reinterpret_cast<const uint32_t *>(p.off)[e];
+      if (cached_group != gi) {  // per-(group, sub-pass) block lists: keep them in shared memory
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.gsub + G.gsub_off);
+        const int n32 = p.n_sub * (int)(sizeof(GroupSubDev) / 4);
+        for (int e = tid; e < n32; e += nthr) reinterpret_cast<uint32_t *>(gsub_s)[e] = src[e];
+        cached_group = gi;
+      }
     }
     __syncthreads();
 
@@ -180,20 +197,21 @@ __global__ void __launch_bounds__(512, 1)
               reinterpret_cast<const uint32_t *>(p.off + (size_t)(s + 1) * kOffTabEntries);
           for (int e = tid; e < kOffTabEntries / 2; e += nthr) dst[e] = src[e];
         }
-        const GroupSubDev &gs = p.gsub[G.gsub_off + s];
+        const GroupSubDev &gs = gsub_s[s];
         const int q0 = p.sub[s].q0, r0 = p.sub[s].rot_begin, r1 = p.sub[s].rot_end;
         const uint32_t *__restrict__ blocks = p.u32 + gs.blocks_off;
-        int chunk_base = 0;
-        for (int sg = 0; sg < gs.n_seg; ++sg) {
-          const int mp = gs.seg[sg].mp, n_items = gs.seg[sg].count * cols;
+        // warps take 32-item chunks round-robin over the concatenated (heavy-first) chunk list
+        int next = warp, chunk_base = 0;
+        const int n_seg = gs.n_seg;
+        for (int sg = 0; sg < n_seg; ++sg) {
+          const int mp = gs.seg[sg].mp, seg_begin = gs.seg[sg].begin;
+          const int n_items = gs.seg[sg].count * cols;
           const int n_chunks = (n_items + 31) >> 5;
-          // warps take 32-item chunks round-robin over the concatenated chunk list
-          int first = (warp - chunk_base % nwarp + nwarp) % nwarp;
-          for (int ch = first; ch < n_chunks; ch += nwarp) {
-            const int item = (ch << 5) + lane;
+          for (; next < chunk_base + n_chunks; next += nwarp) {
+            const int item = ((next - chunk_base) << 5) + lane;
             if (item < n_items) {
-              const int blk = item / cols, col = item - blk * cols;
-              const uint32_t entry = blocks[gs.seg[sg].begin + blk];
+              const int blk = fast_div(item, inv_cols), col = item - blk * cols;
+              const uint32_t entry = blocks[seg_begin + blk];
               process_dispatch<W>(mp, tile, cols, col, entry, offtab, p, r0, r1, q0);
             }
           }
@@ -206,7 +224,7 @@ __global__ void __launch_bounds__(512, 1)
     // ---- store the tile (and fold the per-row phase product in on the last pass)
     if (p.col_stride == 1) {
       for (int e = tid; e < n_el; e += nthr) {
-        const int r = e / cols, j = e - r * cols;
+        const int r = fast_div(e, inv_cols), j = e - r * cols;
         if (j < ncv) {
           double2 v = tile[e];
           const uint32_t row = rowbase + tab[r];
@@ -219,7 +237,7 @@ __global__ void __launch_bounds__(512, 1)
       }
     } else {
       for (int e = tid; e < n_el; e += nthr) {
-        const int j = e / R, r = e - j * R;
+        const int j = fast_div(e, inv_R), r = e - j * R;
         if (j < ncv) {
           double2 v = tile[r * cols + j];
           const uint32_t row = rowbase + tab[r];
@@ -249,7 +267,7 @@ static cudaError_t launch_w(const PassParams &p, int grid, int threads, size_t s
   return cudaGetLastError();
 }
 
-size_t fused_pass_smem_overhead() { return 2 * kOffTabEntries * sizeof(uint16_t); }
+size_t fused_pass_smem_overhead() { return kFusedSmemOverhead; }
 
 cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t tile_bytes,
                               cudaStream_t stream) {

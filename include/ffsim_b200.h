@@ -180,6 +180,14 @@ int ffb_vdot(const void *x_dev, const void *y_dev, int64_t n, void *result_dev, 
 /* y = alpha * x + beta * y, complex scalars */
 int ffb_axpby(ffb_c128 alpha, const void *x_dev, ffb_c128 beta, void *y_dev, int64_t n, void *stream);
 
+/* Launch profiling for bench.py.  Between begin and end every fused-pass, diagonal
+ * and transpose kernel launch is bracketed by CUDA events on its own stream and
+ * every kernel launch of the library is counted.  ffb_profile_end synchronises the
+ * device and writes a JSON object {"<kernel>": {"launches", "timed", "ms", "bytes"}}
+ * (bytes = algorithmic bytes of the timed launches). */
+int ffb_profile_begin(void);
+int ffb_profile_end(char *buf, size_t buflen);
+
 /* Tuning knobs (process-wide; read when a plan is built).  key/value pairs:
  *   "smem_bytes"   shared-memory budget per tile (default: device opt-in max)
  *   "min_cols"     smallest column strip per tile (default 4)

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--norb", type=int, default=16)
     ap.add_argument("--nelec", type=int, nargs=2, default=[5, 5])
     ap.add_argument("--opts", type=str, default="")
+    ap.add_argument("--only-rot", action="store_true")
     args = ap.parse_args()
     norb, nelec = args.norb, tuple(args.nelec)
     for kv in filter(None, args.opts.split(",")):
@@ -55,6 +56,11 @@ def main():
     out["orbital_rotation_alg_GBps"] = 4 * gb / (best / 1e3)
     med, best = timeit(lambda: ffsim.apply_orbital_rotation(vec, (u, None), norb, nelec, copy=False))
     out["alpha_only_ms"] = med
+    if args.only_rot:
+        med, best = timeit(lambda: ffsim.apply_orbital_rotation(vec, (None, u), norb, nelec, copy=False))
+        out["beta_only_ms"] = med
+        print(json.dumps({k: out[k] for k in ("opts", "plan", "orbital_rotation_ms", "alpha_only_ms", "beta_only_ms")}))
+        return
     med, best = timeit(lambda: ffsim.apply_orbital_rotation(vec, (None, u), norb, nelec, copy=False))
     out["beta_only_ms"] = med
     med, best = timeit(lambda: ffsim.apply_diag_coulomb_evolution(vec, mat, 1.0, norb, nelec, copy=False))
