@@ -15,7 +15,7 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libffsim_b200.so")
+LIB_PATH = os.environ.get("FFSIM_B200_LIB") or os.path.join(_HERE, "lib", "libffsim_b200.so")  # env: developer override
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

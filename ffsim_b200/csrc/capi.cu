@@ -14,6 +14,12 @@
 
 using namespace ffb;
 
+#ifdef FFB_DEBUG_KNOBS
+namespace ffb {
+void set_debug_knobs(int v);
+}
+#endif
+
 static_assert(ffb::kMaxLow == ffb::kMaxLowDev, "kMaxLow mismatch");
 
 #define FFB_CUDA(call)                                                                      \
@@ -751,6 +757,13 @@ int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const do
                  coeffs_b ? mb.data() : nullptr, 0, vec_dev, out_dev, accumulate, row0, n_rows,
                  (cudaStream_t)stream);
 }
+
+#ifdef FFB_DEBUG_KNOBS
+int ffb_debug_knobs(int v) {
+  ffb::set_debug_knobs(v);
+  return FFB_OK;
+}
+#endif
 
 int ffb_profile_begin(void) {
   std::lock_guard<std::mutex> lk(g_prof.mu);

@@ -56,8 +56,10 @@ struct PassParams {
   long long total_units;
   GroupLaunch g[kMaxGroups];
   SubMeta sub[kMaxSubPerPass];
-  unsigned char rq[kMaxRotPerPass];  // pair position relative to the pass window
-  double rc[kMaxRotPerPass], rsr[kMaxRotPerPass], rsi[kMaxRotPerPass];
+  // rotation r of the pass: pair position relative to the pass window and (c, s);
+  // one spare slot so that the kernel may prefetch entry r + 1
+  unsigned char rq[kMaxRotPerPass + 8];
+  double rc[kMaxRotPerPass + 1], rsr[kMaxRotPerPass + 1], rsi[kMaxRotPerPass + 1];
 };
 
 }  // namespace ffb

@@ -81,76 +81,118 @@ struct DiagParams {
   int norb, zrep, accumulate;
 };
 
+constexpr int kChunkBits = 6;                  // beta-string bits per lookup table
+constexpr int kChunkSize = 1 << kChunkBits;    // entries per table
+constexpr int kRowsPerWarp = 2;                // alpha rows a warp streams together
+constexpr int kDiagUnroll = 2;
+
+// One warp owns kRowsPerWarp alpha rows at a time: it builds their lookup tables in its
+// private slice of shared memory, then streams the rows together so that the beta string
+// and the beta factor of a column are loaded once for all of them.
 template <class S, bool CONTRACT>
-__global__ void __launch_bounds__(256) diag_kernel(const DiagParams p) {
+__global__ void __launch_bounds__(128, 6) diag_kernel(const DiagParams p) {
   using T = typename S::T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int nch = (p.norb + 7) >> 3;
-  T *pm = reinterpret_cast<T *>(smem_raw) + (size_t)warp * (32 + nch * 256);
-  T *tab = pm + 32;
+  const int nch = (p.norb + kChunkBits - 1) / kChunkBits;
+  const int per_row = 32 + nch * kChunkSize;  // pm[32] then the tables
+  T *wbase = reinterpret_cast<T *>(smem_raw) + (size_t)warp * kRowsPerWarp * per_row;
   const T *__restrict__ rowfac = reinterpret_cast<const T *>(p.rowfac);
   const T *__restrict__ colfac = reinterpret_cast<const T *>(p.colfac);
   const T *__restrict__ mab = reinterpret_cast<const T *>(p.mab);
+  const long long n_groups = (p.n_rows + kRowsPerWarp - 1) / kRowsPerWarp;
   const long long gw = (long long)blockIdx.x * wpb + warp, nw = (long long)gridDim.x * wpb;
 
-  for (long long row = gw; row < p.n_rows; row += nw) {
-    const uint32_t a = p.strings_a[p.row0 + row];
-    const T rf = rowfac ? rowfac[p.row0 + row] : S::one();
-    if (mab) {
-      for (int j = lane; j < p.norb; j += 32) {
-        T acc = S::one();
-        for (int i = 0; i < p.norb; ++i) {
-          const bool bit = (a >> i) & 1u;
-          const T m = mab[i * p.norb + j];
-          if (p.zrep)
-            acc = S::comb(acc, bit ? S::flip(m) : m);
-          else if (bit)
-            acc = S::comb(acc, m);
-        }
-        pm[j] = acc;
-      }
-      __syncwarp();
-      for (int c = 0; c < nch; ++c) {
-        const int nb = min(8, p.norb - 8 * c);
-        for (int e = lane; e < (1 << nb); e += 32) {
-          T acc = (c == 0) ? rf : S::one();
-          for (int j = 0; j < nb; ++j) {
-            const bool bit = (e >> j) & 1;
-            const T m = pm[8 * c + j];
+  for (long long grp = gw; grp < n_groups; grp += nw) {
+    const long long row_first = grp * kRowsPerWarp;
+    T rf[kRowsPerWarp];
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      const long long row = min(row_first + rr, p.n_rows - 1);  // a ragged last group repeats its row
+      rf[rr] = rowfac ? rowfac[p.row0 + row] : S::one();
+      if (mab) {
+        const uint32_t a = p.strings_a[p.row0 + row];
+        T *pm = wbase + rr * per_row, *tab = pm + 32;
+        for (int j = lane; j < p.norb; j += 32) {
+          T acc = S::one();
+          for (int i = 0; i < p.norb; ++i) {
+            const bool bit = (a >> i) & 1u;
+            const T m = mab[i * p.norb + j];
             if (p.zrep)
               acc = S::comb(acc, bit ? S::flip(m) : m);
             else if (bit)
               acc = S::comb(acc, m);
           }
-          tab[c * 256 + e] = acc;
+          pm[j] = acc;
+        }
+        __syncwarp();
+        for (int e = lane; e < nch * kChunkSize; e += 32) {
+          const int c = e >> kChunkBits, bits = e & (kChunkSize - 1);
+          const int nb = min(kChunkBits, p.norb - kChunkBits * c);
+          T acc = (c == 0) ? rf[rr] : S::one();  // the alpha factor rides on the first table
+          for (int j = 0; j < nb; ++j) {
+            const bool bit = (bits >> j) & 1;
+            const T m = pm[kChunkBits * c + j];
+            if (p.zrep)
+              acc = S::comb(acc, bit ? S::flip(m) : m);
+            else if (bit)
+              acc = S::comb(acc, m);
+          }
+          tab[e] = acc;
         }
       }
-      __syncwarp();
     }
-    const double2 *__restrict__ src = p.vec + row * p.dim_b;
-    double2 *__restrict__ dst = p.out + row * p.dim_b;
-#pragma unroll 4
-    for (long long b = lane; b < p.dim_b; b += 32) {
-      const uint32_t s = p.strings_b[b];
-      T f = colfac ? colfac[b] : S::one();
-      if (mab) {
-        f = S::comb(f, tab[s & 255u]);
-        for (int c = 1; c < nch; ++c) f = S::comb(f, tab[c * 256 + ((s >> (8 * c)) & 255u)]);
-      } else {
-        f = S::comb(f, rf);
-      }
-      const double2 v = src[b];
-      if constexpr (CONTRACT) {
-        double2 o = make_double2(f * v.x, f * v.y);
-        if (p.accumulate) {
-          const double2 old = dst[b];
-          o.x += old.x;
-          o.y += old.y;
+    __syncwarp();
+    const int n_valid = (int)min((long long)kRowsPerWarp, p.n_rows - row_first);
+    const double2 *__restrict__ src = p.vec + row_first * p.dim_b;
+    double2 *__restrict__ dst = p.out + row_first * p.dim_b;
+    const T *tab0 = wbase + 32;
+    for (long long b0 = lane; b0 < p.dim_b; b0 += 32 * kDiagUnroll) {
+      uint32_t str[kDiagUnroll];
+      T cf[kDiagUnroll];
+      double2 v[kDiagUnroll][kRowsPerWarp], old[kDiagUnroll][kRowsPerWarp];
+#pragma unroll
+      for (int u = 0; u < kDiagUnroll; ++u) {
+        const long long b = b0 + 32 * u;
+        if (b < p.dim_b) {
+          str[u] = p.strings_b[b];
+          cf[u] = colfac ? colfac[b] : S::one();
+#pragma unroll
+          for (int rr = 0; rr < kRowsPerWarp; ++rr)
+            if (rr < n_valid) {
+              v[u][rr] = src[rr * p.dim_b + b];
+              if (CONTRACT && p.accumulate) old[u][rr] = dst[rr * p.dim_b + b];
+            }
         }
-        dst[b] = o;
-      } else {
-        dst[b] = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+      }
+#pragma unroll
+      for (int u = 0; u < kDiagUnroll; ++u) {
+        const long long b = b0 + 32 * u;
+        if (b < p.dim_b) {
+#pragma unroll
+          for (int rr = 0; rr < kRowsPerWarp; ++rr)
+            if (rr < n_valid) {
+              T f = cf[u];
+              if (mab) {
+                const T *tab = tab0 + rr * per_row;
+                for (int c = 0; c < nch; ++c)
+                  f = S::comb(f, tab[c * kChunkSize + ((str[u] >> (kChunkBits * c)) & (kChunkSize - 1))]);
+              } else {
+                f = S::comb(f, rf[rr]);
+              }
+              double2 o;
+              if constexpr (CONTRACT) {
+                o = make_double2(f * v[u][rr].x, f * v[u][rr].y);
+                if (p.accumulate) {
+                  o.x += old[u][rr].x;
+                  o.y += old[u][rr].y;
+                }
+              } else {
+                o = make_double2(v[u][rr].x * f.x - v[u][rr].y * f.y, v[u][rr].x * f.y + v[u][rr].y * f.x);
+              }
+              dst[rr * p.dim_b + b] = o;
+            }
+        }
       }
     }
     __syncwarp();
@@ -275,12 +317,13 @@ cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t
   p.norb = norb;
   p.zrep = zrep;
   p.accumulate = accumulate;
-  const int threads = 256, wpb = threads / 32;
-  const int nch = (norb + 7) / 8;
+  const int threads = 128, wpb = threads / 32;
+  const int nch = (norb + kChunkBits - 1) / kChunkBits;
   const size_t elem = contract ? sizeof(double) : sizeof(double2);
-  const size_t smem = mab ? (size_t)wpb * (32 + nch * 256) * elem : 0;
-  long long blocks = (n_rows + wpb - 1) / wpb;
-  const long long cap = (long long)sm_count * 8;
+  const size_t smem = mab ? (size_t)wpb * kRowsPerWarp * (32 + nch * kChunkSize) * elem : 0;
+  const long long n_groups = (n_rows + kRowsPerWarp - 1) / kRowsPerWarp;
+  long long blocks = (n_groups + wpb - 1) / wpb;
+  const long long cap = (long long)sm_count * 16;
   if (blocks > cap) blocks = cap;
   cudaError_t e = cudaSuccess;
   if (contract) {

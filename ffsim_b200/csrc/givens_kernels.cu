@@ -19,6 +19,14 @@
 
 namespace ffb {
 
+#ifdef FFB_DEBUG_KNOBS
+// what-if timing switches (developer builds only; results are wrong when any is set)
+__device__ int g_debug_knobs = 0;
+#define FFB_KNOB(bit) (g_debug_knobs & (bit))
+#else
+#define FFB_KNOB(bit) 0
+#endif
+
 // ---------------------------------------------------------------- constexpr combinatorics
 __host__ __device__ constexpr int cbinom(int n, int k) {
   if (k < 0 || k > n) return 0;
@@ -93,17 +101,31 @@ __device__ __forceinline__ void process_item(double2 *__restrict__ tile, int col
   const int base = (int)(entry & 0xFFFFFFu);
   const uint16_t *o = offtab + (entry >> 24) * kOffRow + cclass_offset(W, M);
   double2 a[N];
-  int idx[N];
+  unsigned idx2[(N + 1) / 2];  // tile indices, two 16-bit values per register
 #pragma unroll
   for (int t = 0; t < N; ++t) {
-    idx[t] = (base + (int)o[t]) * cols + col;
-    a[t] = tile[idx[t]];
+    const unsigned i = (unsigned)((base + (int)o[t]) * cols + col);
+    a[t] = tile[i];
+    if (t & 1)
+      idx2[t >> 1] |= i << 16;
+    else
+      idx2[t >> 1] = i;
   }
-  for (int r = r0; r < r1; ++r) {
-    rot_dispatch<W, M>(a, (int)p.rq[r] - q0, p.rc[r], p.rsr[r], p.rsi[r]);
+  // software-pipelined coefficient fetch: the next rotation's (q, c, s) is loaded from the
+  // constant bank while the current one is applied (the arrays have a spare slot at the end)
+  int q = (int)p.rq[r0] - q0;
+  double c = p.rc[r0], sr = p.rsr[r0], si = p.rsi[r0];
+  for (int r = r0; r < (FFB_KNOB(4) ? r0 : r1); ++r) {
+    const int qn = (int)p.rq[r + 1] - q0;
+    const double cn = p.rc[r + 1], srn = p.rsr[r + 1], sin_ = p.rsi[r + 1];
+    rot_dispatch<W, M>(a, q, c, sr, si);
+    q = qn;
+    c = cn;
+    sr = srn;
+    si = sin_;
   }
 #pragma unroll
-  for (int t = 0; t < N; ++t) tile[idx[t]] = a[t];
+  for (int t = 0; t < N; ++t) tile[(t & 1) ? (idx2[t >> 1] >> 16) : (idx2[t >> 1] & 0xFFFFu)] = a[t];
 }
 
 template <int W, int M = 1>
@@ -123,10 +145,64 @@ constexpr int kOffTabEntries = kMaxLowDev * kOffRow;  // u16 entries of one sub-
 constexpr size_t kFusedSmemOverhead =
     ((2 * kOffTabEntries * sizeof(uint16_t) + kMaxSubPerPass * sizeof(GroupSubDev)) + 15) / 16 * 16;
 
+// 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, no stall at issue
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // n / d for n * d < 2^32 with a precomputed inv = 0xFFFFFFFF / d + 1 (which wraps to 0 for d == 1)
 __device__ __forceinline__ int fast_div(int n, unsigned inv) {
   return inv ? (int)__umulhi((unsigned)n, inv) : n;
 }
+
+// One 32-item chunk of register blocks, as seen by one lane.
+struct ChunkWork {
+  uint32_t entry;
+  int mp;   // class (electrons in the register block); 0 = nothing to do for this lane
+  int col;
+};
+
+// The g-th chunk of the concatenated (heavy classes first) chunk list of a sub-pass.
+__device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const uint32_t *__restrict__ u32,
+                                                 int g, int lane, int cols, unsigned inv_cols) {
+  ChunkWork w;
+  w.entry = 0;
+  w.mp = 0;
+  w.col = 0;
+  int base = 0;
+  for (int sg = 0; sg < gs.n_seg; ++sg) {
+    const int n_items = gs.seg[sg].count * cols;
+    const int n_chunks = (n_items + 31) >> 5;
+    if (g < base + n_chunks) {
+      const int item = ((g - base) << 5) + lane;
+      if (item < n_items) {
+        const int blk = fast_div(item, inv_cols);
+        w.col = item - blk * cols;
+        w.mp = gs.seg[sg].mp;
+        w.entry = u32[gs.blocks_off + gs.seg[sg].begin + blk];
+      }
+      return w;
+    }
+    base += n_chunks;
+  }
+  return w;
+}
+
+__device__ __forceinline__ int total_chunks(const GroupSubDev &gs, int cols) {
+  int n = 0;
+  for (int sg = 0; sg < gs.n_seg; ++sg) n += (gs.seg[sg].count * cols + 31) >> 5;
+  return n;
+}
+
+// k-th chunk position of warp `warp` when chunks are dealt to warps in snake order
+// (0..nw-1, nw-1..0, ...): with the list sorted by decreasing cost this balances the warps.
+__device__ __forceinline__ int snake_pos(int k, int warp, int nwarp) {
+  return k * nwarp + ((k & 1) ? (nwarp - 1 - warp) : warp);
+}
+
+constexpr int kLoadUnroll = 8;
 
 template <int W>
 __global__ void __launch_bounds__(512, 1)
@@ -135,6 +211,7 @@ __global__ void __launch_bounds__(512, 1)
   uint16_t *offbuf = reinterpret_cast<uint16_t *>(smem_raw);  // 2 x kOffTabEntries
   GroupSubDev *gsub_s = reinterpret_cast<GroupSubDev *>(smem_raw + 2 * kOffTabEntries * sizeof(uint16_t));
   double2 *tile = reinterpret_cast<double2 *>(smem_raw + kFusedSmemOverhead);
+  __shared__ int chunk_ctr[2];
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -157,95 +234,119 @@ __global__ void __launch_bounds__(512, 1)
     const uint32_t *__restrict__ tab =
         p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
     const int n_el = R * cols;
+    const bool row_major = p.col_stride == 1;  // batch index contiguous in memory
 
-    // ---- load the tile
-    if (p.col_stride == 1) {
-      for (int e = tid; e < n_el; e += nthr) {
-        const int r = fast_div(e, inv_cols), j = e - r * cols;
-        double2 v = make_double2(0.0, 0.0);
-        if (j < ncv) v = data[(long long)(rowbase + tab[r]) * p.row_stride + col0 + j];
-        tile[e] = v;
+    // ---- load the tile: kLoadUnroll independent (table -> global -> shared) chains per thread
+    for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
+      double2 v[kLoadUnroll];
+      int dst[kLoadUnroll];
+#pragma unroll
+      for (int u = 0; u < kLoadUnroll; ++u) {
+        const int e = e0 + u * nthr;
+        v[u] = make_double2(0.0, 0.0);
+        dst[u] = -1;
+        if (e < n_el) {
+          int r, j;
+          if (row_major) {
+            r = fast_div(e, inv_cols);
+            j = e - r * cols;
+          } else {
+            j = fast_div(e, inv_R);
+            r = e - j * R;
+          }
+          dst[u] = r * cols + j;
+          if (j < ncv && !FFB_KNOB(2))
+            v[u] = data[(long long)(rowbase + tab[r]) * p.row_stride + (col0 + j) * p.col_stride];
+        }
       }
-    } else {
-      for (int e = tid; e < n_el; e += nthr) {
-        const int j = fast_div(e, inv_R), r = e - j * R;
-        double2 v = make_double2(0.0, 0.0);
-        if (j < ncv)
-          v = data[(long long)(rowbase + tab[r]) * p.row_stride + (col0 + j) * p.col_stride];
-        tile[r * cols + j] = v;
-      }
+#pragma unroll
+      for (int u = 0; u < kLoadUnroll; ++u)
+        if (dst[u] >= 0) tile[dst[u]] = v[u];
     }
-    if (G.has_blocks && p.n_sub > 0) {
-      for (int e = tid; e < kOffTabEntries / 2; e += nthr)
-        reinterpret_cast<uint32_t *>(offbuf)[e] = reinterpret_cast<const uint32_t *>(p.off)[e];
+    const bool work = G.has_blocks && p.n_sub > 0;
+    if (work) {
+      for (int e = tid; e < kOffTabEntries / 8; e += nthr)
+        cp_async16(offbuf + 8 * e, p.off + 8 * e);
       if (cached_group != gi) {  // per-(group, sub-pass) block lists: keep them in shared memory
         const uint32_t *src = reinterpret_cast<const uint32_t *>(p.gsub + G.gsub_off);
         const int n32 = p.n_sub * (int)(sizeof(GroupSubDev) / 4);
         for (int e = tid; e < n32; e += nthr) reinterpret_cast<uint32_t *>(gsub_s)[e] = src[e];
-        cached_group = gi;
       }
+      if (tid == 0) chunk_ctr[0] = nwarp;
+      cp_async_wait_all();
     }
     __syncthreads();
+    cached_group = work ? gi : cached_group;
 
     // ---- sub-passes
-    if (G.has_blocks) {
+    if (work) {
+      ChunkWork cur = fetch_chunk(gsub_s[0], p.u32, warp, lane, cols, inv_cols);
       for (int s = 0; s < p.n_sub; ++s) {
         const uint16_t *offtab = offbuf + (s & 1) * kOffTabEntries;
-        if (s + 1 < p.n_sub) {  // prefetch the next sub-pass's offset table
-          uint32_t *dst = reinterpret_cast<uint32_t *>(offbuf + ((s + 1) & 1) * kOffTabEntries);
-          const uint32_t *src =
-              reinterpret_cast<const uint32_t *>(p.off + (size_t)(s + 1) * kOffTabEntries);
-          for (int e = tid; e < kOffTabEntries / 2; e += nthr) dst[e] = src[e];
+        if (s + 1 < p.n_sub) {  // prefetch the next sub-pass's offset table (lands before the barrier)
+          uint16_t *dst = offbuf + ((s + 1) & 1) * kOffTabEntries;
+          const uint16_t *src = p.off + (size_t)(s + 1) * kOffTabEntries;
+          for (int e = tid; e < kOffTabEntries / 8; e += nthr) cp_async16(dst + 8 * e, src + 8 * e);
         }
         const GroupSubDev &gs = gsub_s[s];
         const int q0 = p.sub[s].q0, r0 = p.sub[s].rot_begin, r1 = p.sub[s].rot_end;
-        const uint32_t *__restrict__ blocks = p.u32 + gs.blocks_off;
-        // warps take 32-item chunks round-robin over the concatenated (heavy-first) chunk list
-        int next = warp, chunk_base = 0;
-        const int n_seg = gs.n_seg;
-        for (int sg = 0; sg < n_seg; ++sg) {
-          const int mp = gs.seg[sg].mp, seg_begin = gs.seg[sg].begin;
-          const int n_items = gs.seg[sg].count * cols;
-          const int n_chunks = (n_items + 31) >> 5;
-          for (; next < chunk_base + n_chunks; next += nwarp) {
-            const int item = ((next - chunk_base) << 5) + lane;
-            if (item < n_items) {
-              const int blk = fast_div(item, inv_cols), col = item - blk * cols;
-              const uint32_t entry = blocks[seg_begin + blk];
-              process_dispatch<W>(mp, tile, cols, col, entry, offtab, p, r0, r1, q0);
-            }
+        const int n_chunks = total_chunks(gs, cols);
+        // chunks 0..nwarp-1 are owned statically (their descriptors were prefetched before the
+        // previous barrier); the rest are handed out dynamically, heaviest first
+        int *ctr = &chunk_ctr[s & 1];
+        if (tid == 0) chunk_ctr[(s + 1) & 1] = nwarp;
+        int g = warp;
+        while (true) {
+          const bool have = g < n_chunks;
+          int g_next = n_chunks;
+          if (have) {
+            if (lane == 0) g_next = atomicAdd(ctr, 1);
+            g_next = __shfl_sync(0xffffffffu, g_next, 0);
           }
-          chunk_base += n_chunks;
+          ChunkWork nxt;
+          if (g_next < n_chunks) {
+            nxt = fetch_chunk(gs, p.u32, g_next, lane, cols, inv_cols);
+          } else if (s + 1 < p.n_sub) {
+            nxt = fetch_chunk(gsub_s[s + 1], p.u32, warp, lane, cols, inv_cols);
+          } else {
+            nxt.entry = 0;
+            nxt.mp = 0;
+            nxt.col = 0;
+          }
+          if (have && cur.mp && !FFB_KNOB(8))
+            process_dispatch<W>(cur.mp, tile, cols, cur.col, cur.entry, offtab, p, r0, r1, q0);
+          cur = nxt;
+          if (g_next >= n_chunks) break;
+          g = g_next;
         }
-        __syncthreads();
+        cp_async_wait_all();
+        if (!FFB_KNOB(1)) __syncthreads();
       }
     }
 
     // ---- store the tile (and fold the per-row phase product in on the last pass)
-    if (p.col_stride == 1) {
-      for (int e = tid; e < n_el; e += nthr) {
-        const int r = fast_div(e, inv_cols), j = e - r * cols;
-        if (j < ncv) {
-          double2 v = tile[e];
-          const uint32_t row = rowbase + tab[r];
-          if (rowphase) {
-            const double2 f = rowphase[row];
-            v = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+    for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
+#pragma unroll
+      for (int u = 0; u < kLoadUnroll; ++u) {
+        const int e = e0 + u * nthr;
+        if (e < n_el) {
+          int r, j;
+          if (row_major) {
+            r = fast_div(e, inv_cols);
+            j = e - r * cols;
+          } else {
+            j = fast_div(e, inv_R);
+            r = e - j * R;
           }
-          data[(long long)row * p.row_stride + col0 + j] = v;
-        }
-      }
-    } else {
-      for (int e = tid; e < n_el; e += nthr) {
-        const int j = fast_div(e, inv_R), r = e - j * R;
-        if (j < ncv) {
-          double2 v = tile[r * cols + j];
-          const uint32_t row = rowbase + tab[r];
-          if (rowphase) {
-            const double2 f = rowphase[row];
-            v = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+          if (j < ncv && !FFB_KNOB(2)) {
+            double2 v = tile[r * cols + j];
+            const uint32_t row = rowbase + tab[r];
+            if (rowphase) {
+              const double2 f = rowphase[row];
+              v = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+            }
+            data[(long long)row * p.row_stride + (col0 + j) * p.col_stride] = v;
           }
-          data[(long long)row * p.row_stride + (col0 + j) * p.col_stride] = v;
         }
       }
     }
@@ -268,6 +369,10 @@ static cudaError_t launch_w(const PassParams &p, int grid, int threads, size_t s
 }
 
 size_t fused_pass_smem_overhead() { return kFusedSmemOverhead; }
+
+#ifdef FFB_DEBUG_KNOBS
+void set_debug_knobs(int v) { cudaMemcpyToSymbol(g_debug_knobs, &v, sizeof(int)); }
+#endif
 
 cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t tile_bytes,
                               cudaStream_t stream) {

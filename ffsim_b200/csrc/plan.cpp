@@ -42,6 +42,7 @@ int max_window(int norb, int nocc, const PlanOptions &opt) {
     uint64_t maxR = 0;
     for (int m = mlo; m <= mhi; ++m) maxR = std::max(maxR, binom(W, m));
     if (maxR >= 65536) continue;  // block offsets are 16-bit
+    if ((int64_t)maxR * std::max(1, opt.min_cols) >= 65536) continue;  // tile indices are 16-bit
     if ((int64_t)maxR * std::max(1, opt.min_cols) <= budget_amps) return W;
   }
   return std::min(norb, 2);
@@ -75,6 +76,65 @@ static std::vector<int> minus(const std::vector<int> &a, const std::vector<int> 
   return out;
 }
 
+// Tile a rotation sequence (pair positions q, relative to a span of `span` orbitals) with
+// windows of width `width`: returns groups in execution order; each group is a window
+// start and the indices of the rotations it applies (a dependency-closed set).
+// Greedy "take the fullest window" strands a few rotations in groups of their own, and a
+// group here costs a sweep over the state (level 1) or over the tile (level 2), so a small
+// beam search over the window choices minimises the number of groups instead.
+struct Group {
+  int start;
+  std::vector<int> members;
+};
+
+static std::vector<Group> tile_sequence(const std::vector<int> &index, const std::vector<int> &q,
+                                        int span, int width, size_t cap, size_t max_groups) {
+  struct State {
+    std::vector<int> remaining;
+    std::vector<Group> groups;
+  };
+  const size_t kBeam = 12;
+  std::vector<State> beam(1);
+  beam[0].remaining = index;
+  if (index.empty()) return {};
+  for (size_t depth = 0; depth < 4 * index.size() + 4; ++depth) {
+    std::vector<State> next;
+    for (const State &st : beam) {
+      // candidate windows, deduplicated by the set they admit
+      std::vector<std::vector<int>> seen;
+      for (int start = 0; start + width <= span; ++start) {
+        std::vector<int> got = admit(st.remaining, q, start, width, cap);
+        if (got.empty()) continue;
+        bool dup = false;
+        for (const auto &o : seen) dup = dup || o == got;
+        if (dup) continue;
+        seen.push_back(got);
+        State ns;
+        ns.remaining = minus(st.remaining, got);
+        ns.groups = st.groups;
+        ns.groups.push_back({start, std::move(got)});
+        next.push_back(std::move(ns));
+      }
+    }
+    assert(!next.empty());
+    // finished states win; otherwise keep the states with the fewest rotations left
+    std::stable_sort(next.begin(), next.end(), [](const State &a, const State &b) {
+      return a.remaining.size() < b.remaining.size();
+    });
+    if (next[0].remaining.empty() || next[0].groups.size() >= max_groups) return next[0].groups;
+    // drop duplicates (same remaining set) and cut to the beam width
+    std::vector<State> cut;
+    for (State &ns : next) {
+      bool dup = false;
+      for (const State &o : cut) dup = dup || o.remaining == ns.remaining;
+      if (!dup) cut.push_back(std::move(ns));
+      if (cut.size() == kBeam) break;
+    }
+    beam.swap(cut);
+  }
+  return beam[0].groups;
+}
+
 SideSchedule build_schedule(int norb, int nocc, const std::vector<int> &q, const PlanOptions &opt) {
   SideSchedule sched;
   sched.norb = norb;
@@ -83,64 +143,43 @@ SideSchedule build_schedule(int norb, int nocc, const std::vector<int> &q, const
   const int W = max_window(norb, nocc, opt);
   const int w = std::max(2, std::min({opt.sub_window, kMaxSubWindow, W}));
 
-  std::vector<int> remaining(q.size());
-  for (size_t g = 0; g < q.size(); ++g) remaining[g] = (int)g;
-
+  std::vector<int> all(q.size());
+  for (size_t g = 0; g < q.size(); ++g) all[g] = (int)g;
+  std::vector<int> remaining = all;
   while (!remaining.empty()) {
-    std::vector<int> best;
-    int best_lo = 0;
-    for (int lo = 0; lo + W <= norb; ++lo) {
-      std::vector<int> got = admit(remaining, q, lo, W, kMaxRotPerPass);
-      if (got.size() > best.size()) {
-        best.swap(got);
-        best_lo = lo;
+    // level 1: sweeps over the state.  (Re-planned from the rotations still left, so a pass
+    // that had to hand rotations back -- see below -- is followed by a consistent schedule.)
+    std::vector<Group> passes = tile_sequence(remaining, q, norb, W, kMaxRotPerPass, 1u << 30);
+    assert(!passes.empty());
+    bool handed_back = false;
+    for (const Group &pg : passes) {
+      PassSchedule pass;
+      pass.lo = pg.start;
+      pass.W = W;
+      // level 2: register-block sub-passes inside the tile
+      std::vector<int> qrel(q.size(), 0);
+      for (int g : pg.members) qrel[g] = q[g] - pg.start;
+      std::vector<Group> subs = tile_sequence(pg.members, qrel, W, w, 1u << 30, kMaxSubPerPass);
+      std::vector<int> done;
+      for (const Group &sg : subs) {
+        SubPass sp;
+        sp.q0 = sg.start;
+        sp.w = w;
+        sp.rot_begin = (int)pass.rot_index.size();
+        pass.rot_index.insert(pass.rot_index.end(), sg.members.begin(), sg.members.end());
+        sp.rot_end = (int)pass.rot_index.size();
+        pass.subs.push_back(sp);
+        done.insert(done.end(), sg.members.begin(), sg.members.end());
+      }
+      std::sort(done.begin(), done.end());
+      remaining = minus(remaining, done);
+      sched.passes.push_back(std::move(pass));
+      if (done.size() != pg.members.size()) {  // out of sub-pass slots: re-plan the rest
+        handed_back = true;
+        break;
       }
     }
-    assert(!best.empty());
-    PassSchedule pass;
-    pass.lo = best_lo;
-    pass.W = W;
-    pass.rot_index = best;
-    remaining = minus(remaining, best);
-
-    // level 2: order the pass's rotations into register-block sub-passes.
-    std::vector<int> qrel(best.size());
-    for (size_t t = 0; t < best.size(); ++t) qrel[t] = q[best[t]] - best_lo;
-    std::vector<int> rem2(best.size());
-    for (size_t t = 0; t < best.size(); ++t) rem2[t] = (int)t;
-    std::vector<int> order;
-    while (!rem2.empty()) {
-      std::vector<int> b2;
-      int b2_q0 = 0;
-      for (int q0 = 0; q0 + w <= W; ++q0) {
-        std::vector<int> got = admit(rem2, qrel, q0, w, 1u << 30);
-        if (got.size() > b2.size()) {
-          b2.swap(got);
-          b2_q0 = q0;
-        }
-      }
-      assert(!b2.empty());
-      SubPass sp;
-      sp.q0 = b2_q0;
-      sp.w = w;
-      sp.rot_begin = (int)order.size();
-      for (int t : b2) order.push_back(best[t]);
-      sp.rot_end = (int)order.size();
-      pass.subs.push_back(sp);
-      rem2 = minus(rem2, b2);
-      if ((int)pass.subs.size() == kMaxSubPerPass && !rem2.empty()) {
-        // out of sub-pass slots: hand the rest back to a later pass
-        std::vector<int> back;
-        for (int t : rem2) back.push_back(best[t]);
-        std::vector<int> merged;
-        std::merge(back.begin(), back.end(), remaining.begin(), remaining.end(),
-                   std::back_inserter(merged));
-        remaining.swap(merged);
-        rem2.clear();
-      }
-    }
-    pass.rot_index = order;
-    sched.passes.push_back(std::move(pass));
+    if (!handed_back) break;
   }
   return sched;
 }

@@ -1,0 +1,38 @@
+"""What-if timing with the developer build (scripts/build_dbg.sh): which phase of the fused
+kernel costs what.  knobs: 1 = no sub-pass barriers, 2 = no global load/store, 4 = no rotation
+math, 8 = no register-block processing at all."""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ["FFSIM_B200_LIB"] = os.path.join(ROOT, "build", "dbg", "libffsim_b200.so")
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import ffsim_b200 as ffsim
+from ffsim_b200 import _lib
+
+norb, nelec = int(sys.argv[1]), (int(sys.argv[2]), int(sys.argv[3]))
+for kv in filter(None, (sys.argv[4] if len(sys.argv) > 4 else "").split(",")):
+    k, v = kv.split("=")
+    _lib.set_option(k, int(v))
+_lib.lib.ffb_debug_knobs.argtypes = [ctypes.c_int]
+u = ffsim.random.random_unitary(norb, seed=1)
+vec = torch.randn(ffsim.dim(norb, nelec), dtype=torch.complex128, device="cuda")
+res = {}
+for knobs in (0, 2, 4, 8, 6, 10):
+    _lib.lib.ffb_debug_knobs(knobs)
+    ts = []
+    for it in range(6):
+        vec.normal_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ffsim.apply_orbital_rotation(vec, (u, None), norb, nelec, copy=False)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    res[knobs] = round(float(np.median(ts[2:])), 4)
+print(json.dumps(res))
