@@ -36,12 +36,30 @@ def stream_ptr() -> int:
 class Kind:
     """How the caller handed the vector over, so that it gets the same kind back."""
 
-    __slots__ = ("numpy", "torch_cpu", "device")
+    __slots__ = ("numpy", "torch_cpu", "device", "sharded")
 
-    def __init__(self, numpy=False, torch_cpu=False, device=None):
+    def __init__(self, numpy=False, torch_cpu=False, device=None, sharded=False):
         self.numpy = numpy
         self.torch_cpu = torch_cpu
         self.device = device
+        self.sharded = sharded
+
+
+def is_sharded(vec: Any) -> bool:
+    from ffsim_b200.distributed import ShardedVector
+
+    return isinstance(vec, ShardedVector)
+
+
+def local_block(t, dim_a: int):
+    """(tensor holding the locally stored alpha rows, first row, number of rows)."""
+    if is_sharded(t):
+        return t.local, t.row0, t.n_rows
+    return t, 0, dim_a
+
+
+def empty_like(t):
+    return t.empty_like() if is_sharded(t) else torch.empty_like(t)
 
 
 def to_device(vec: Any, *, copy: bool) -> tuple[torch.Tensor, Kind]:
@@ -51,6 +69,8 @@ def to_device(vec: Any, *, copy: bool) -> tuple[torch.Tensor, Kind]:
     input); CUDA tensors are cloned only when ``copy`` is set.
     """
     require_cuda()
+    if is_sharded(vec):  # row-sharded multi-GPU state: stays sharded
+        return (vec.clone() if copy else vec), Kind(sharded=True)
     if isinstance(vec, torch.Tensor):
         if vec.is_cuda:
             with torch.cuda.device(vec.device):
@@ -95,7 +115,9 @@ def _download(t: torch.Tensor) -> torch.Tensor:
     return t.cpu()
 
 
-def from_device(t: torch.Tensor, kind: Kind):
+def from_device(t, kind: Kind):
+    if kind.sharded:
+        return t
     if kind.numpy:
         return _download(t).numpy()
     if kind.torch_cpu:

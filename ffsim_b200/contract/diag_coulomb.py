@@ -41,13 +41,15 @@ def _get_mats(mat: Any, norb: int, z_representation: bool):
 def _contract_device(t, out, mats, norb, nelec, z_representation, accumulate) -> None:
     aa, ab, bb = mats
     ta, tb = get_tables(norb, nelec[0]), get_tables(norb, nelec[1])
-    with torch.cuda.device(t.device):
+    data, row0, n_rows = _device.local_block(t, ta.dim)
+    out_data, _, _ = _device.local_block(out, ta.dim)
+    with torch.cuda.device(data.device):
         _device.sync_device()
         _lib.check(
             _lib.lib.ffb_contract_diag_coulomb(
                 ta.handle, tb.handle, _lib.ptr(aa), _lib.ptr(ab), _lib.ptr(bb),
-                int(bool(z_representation)), t.data_ptr(), out.data_ptr(), int(bool(accumulate)),
-                0, ta.dim, _device.stream_ptr(),
+                int(bool(z_representation)), data.data_ptr(), out_data.data_ptr(), int(bool(accumulate)),
+                row0, n_rows, _device.stream_ptr(),
             )
         )
 
@@ -64,7 +66,7 @@ def contract_diag_coulomb(
     mats = _get_mats(mat, norb, z_representation)
     t, kind = _device.to_device(vec, copy=False)
     _check_dim(t, norb, nelec)
-    out = torch.empty_like(t)
+    out = _device.empty_like(t)
     _contract_device(t, out, mats, norb, nelec, z_representation, accumulate=False)
     return _device.from_device(out, kind)
 
@@ -77,8 +79,8 @@ def diag_coulomb_linop(
     dim = math.comb(norb, nelec[0]) * math.comb(norb, nelec[1])
     mats = _get_mats(mat, norb, z_representation)
 
-    def matvec(t: torch.Tensor) -> torch.Tensor:
-        out = torch.empty_like(t)
+    def matvec(t):
+        out = _device.empty_like(t)
         if orbital_rotation is None:
             _contract_device(t, out, mats, norb, nelec, z_representation, accumulate=False)
             return out

@@ -23,26 +23,26 @@ class DeviceLinearOperator(scipy.sparse.linalg.LinearOperator):
         self._device_matvec = device_matvec  # maps a 1-D CUDA tensor to a NEW 1-D CUDA tensor
 
     # --- tensors
-    def matvec_device(self, vec: torch.Tensor) -> torch.Tensor:
+    def matvec_device(self, vec):
         if vec.numel() != self.shape[1]:
             raise ValueError(f"dimension mismatch: {vec.numel()} vs {self.shape[1]}")
         t, kind = _device.to_device(vec, copy=False)
         return _device.from_device(self._device_matvec(t), kind)
 
     def matvec(self, x):
-        if isinstance(x, torch.Tensor):
+        if isinstance(x, torch.Tensor) or _device.is_sharded(x):
             return self.matvec_device(x)
         return super().matvec(x)
 
     rmatvec_device = matvec_device  # Hermitian operators only (rmatvec=matvec in the reference)
 
     def dot(self, x):
-        if isinstance(x, torch.Tensor):
+        if isinstance(x, torch.Tensor) or _device.is_sharded(x):
             return self.matvec_device(x)
         return super().dot(x)
 
     def __matmul__(self, x):
-        if isinstance(x, torch.Tensor):
+        if isinstance(x, torch.Tensor) or _device.is_sharded(x):
             return self.matvec_device(x)
         return super().__matmul__(x)
 

@@ -15,12 +15,14 @@ from ffsim_b200.gates.orbital_rotation import _check_dim, _rotate_device
 
 def _contract_device(t, out, coeffs: np.ndarray, norb, nelec, accumulate) -> None:
     ta, tb = get_tables(norb, nelec[0]), get_tables(norb, nelec[1])
-    with torch.cuda.device(t.device):
+    data, row0, n_rows = _device.local_block(t, ta.dim)
+    out_data, _, _ = _device.local_block(out, ta.dim)
+    with torch.cuda.device(data.device):
         _device.sync_device()
         _lib.check(
             _lib.lib.ffb_contract_num_op_sum(
-                ta.handle, tb.handle, _lib.ptr(coeffs), _lib.ptr(coeffs), t.data_ptr(), out.data_ptr(),
-                int(bool(accumulate)), 0, ta.dim, _device.stream_ptr(),
+                ta.handle, tb.handle, _lib.ptr(coeffs), _lib.ptr(coeffs), data.data_ptr(), out_data.data_ptr(),
+                int(bool(accumulate)), row0, n_rows, _device.stream_ptr(),
             )
         )
 
@@ -42,7 +44,7 @@ def contract_num_op_sum(vec, coeffs, norb: int, nelec: tuple[int, int]):
     c = _coeffs(coeffs, norb)
     t, kind = _device.to_device(vec, copy=False)
     _check_dim(t, norb, nelec)
-    out = torch.empty_like(t)
+    out = _device.empty_like(t)
     _contract_device(t, out, c, norb, nelec, accumulate=False)
     return _device.from_device(out, kind)
 
@@ -54,8 +56,8 @@ def num_op_sum_linop(coeffs, norb: int, nelec: tuple[int, int], *, orbital_rotat
     c = _coeffs(coeffs, norb)
     rot = None if orbital_rotation is None else _device.as_host_matrix(orbital_rotation)
 
-    def matvec(t: torch.Tensor) -> torch.Tensor:
-        out = torch.empty_like(t)
+    def matvec(t):
+        out = _device.empty_like(t)
         if rot is None:
             _contract_device(t, out, c, norb, nelec, accumulate=False)
             return out

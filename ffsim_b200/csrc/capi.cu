@@ -549,6 +549,22 @@ int ffb_apply_orbital_rotation_rows(ffb_plan *p, int side, void *mat_dev, int64_
   return apply_side(p, side, mat_dev, n_cols, ld, 1, (cudaStream_t)stream);
 }
 
+int ffb_apply_orbital_rotation_strided(ffb_plan *p, int side, void *data_dev, int64_t n_batch,
+                                       int64_t row_stride, int64_t col_stride, void *stream) {
+  if (!p || (side != 0 && side != 1))
+    return fail(FFB_EINVAL, "ffb_apply_orbital_rotation_strided: bad argument");
+  if (!data_dev && n_batch > 0) return fail(FFB_EINVAL, "ffb_apply_orbital_rotation_strided: NULL data");
+  if (row_stride != 1 && col_stride != 1)
+    return fail(FFB_EINVAL, "ffb_apply_orbital_rotation_strided: one of the strides must be 1");
+  if (p->side[side].active) {
+    int rc = ensure_device_strings(p->side[side].tables);
+    if (rc != FFB_OK) return rc;
+  }
+  return apply_side(p, side, data_dev, n_batch, row_stride, col_stride, (cudaStream_t)stream);
+}
+
+int ffb_plan_beta_in_place(const ffb_plan *p) { return p && !p->beta_transposed ? 1 : 0; }
+
 int ffb_apply_orbital_rotation(ffb_plan *p, void *vec_dev, void *workspace_dev, void *stream) {
   if (!p) return fail(FFB_EINVAL, "ffb_apply_orbital_rotation: NULL plan");
   if (p->dim_a * p->dim_b == 0) return FFB_OK;

@@ -51,15 +51,16 @@ def _get_mat_exp(mat: Any, time: float, norb: int, z_representation: bool):
     return same_spin(mat_aa), cross(mat_ab), same_spin(mat_bb)
 
 
-def _evolve_device(t: torch.Tensor, mats, norb: int, nelec: tuple[int, int], z_representation: bool) -> None:
+def _evolve_device(t, mats, norb: int, nelec: tuple[int, int], z_representation: bool) -> None:
     aa, ab, bb = mats
     ta, tb = get_tables(norb, nelec[0]), get_tables(norb, nelec[1])
-    with torch.cuda.device(t.device):
+    data, row0, n_rows = _device.local_block(t, ta.dim)
+    with torch.cuda.device(data.device):
         _device.sync_device()
         _lib.check(
             _lib.lib.ffb_apply_diag_coulomb_evolution(
                 ta.handle, tb.handle, _lib.ptr(aa), _lib.ptr(ab), _lib.ptr(bb),
-                int(bool(z_representation)), t.data_ptr(), 0, ta.dim, _device.stream_ptr(),
+                int(bool(z_representation)), data.data_ptr(), row0, n_rows, _device.stream_ptr(),
             )
         )
 

@@ -30,13 +30,14 @@ def _get_phases(coeffs, time: float):
     return ph(coeffs_a), ph(coeffs_b)
 
 
-def _evolve_device(t: torch.Tensor, phases_a, phases_b, norb: int, nelec: tuple[int, int]) -> None:
+def _evolve_device(t, phases_a, phases_b, norb: int, nelec: tuple[int, int]) -> None:
     ta, tb = get_tables(norb, nelec[0]), get_tables(norb, nelec[1])
-    with torch.cuda.device(t.device):
+    data, row0, n_rows = _device.local_block(t, ta.dim)
+    with torch.cuda.device(data.device):
         _device.sync_device()
         _lib.check(
             _lib.lib.ffb_apply_num_op_sum_evolution(
-                ta.handle, tb.handle, _lib.ptr(phases_a), _lib.ptr(phases_b), t.data_ptr(), 0, ta.dim,
+                ta.handle, tb.handle, _lib.ptr(phases_a), _lib.ptr(phases_b), data.data_ptr(), row0, n_rows,
                 _device.stream_ptr(),
             )
         )

@@ -100,8 +100,13 @@ def get_plan(norb: int, nelec: tuple[int, int], mat_a, mat_b) -> _Plan:
     return plan
 
 
-def _rotate_device(t: torch.Tensor, mat_a, mat_b, norb: int, nelec: tuple[int, int]) -> None:
-    """Rotate the device vector ``t`` in place."""
+def _rotate_device(t, mat_a, mat_b, norb: int, nelec: tuple[int, int]) -> None:
+    """Rotate the device vector ``t`` in place (a CUDA tensor or a ShardedVector)."""
+    if _device.is_sharded(t):
+        from ffsim_b200 import distributed
+
+        distributed.rotate(t, mat_a, mat_b)
+        return
     with torch.cuda.device(t.device):
         plan = get_plan(norb, nelec, mat_a, mat_b)
         ws_bytes = plan.workspace_bytes()
@@ -113,9 +118,11 @@ def _rotate_device(t: torch.Tensor, mat_a, mat_b, norb: int, nelec: tuple[int, i
         )
 
 
-def _check_dim(t: torch.Tensor, norb: int, nelec) -> None:
+def _check_dim(t, norb: int, nelec) -> None:
     from ffsim_b200.states import dim
 
+    if _device.is_sharded(t) and (t.norb != norb or t.nelec != tuple(nelec)):
+        raise ValueError(f"sharded vector was built for norb={t.norb}, nelec={t.nelec}")
     d = dim(norb, nelec)
     if t.numel() != d:
         raise ValueError(f"vec has {t.numel()} entries, expected {d} for norb={norb}, nelec={nelec}")

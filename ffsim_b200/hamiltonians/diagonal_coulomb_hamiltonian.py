@@ -18,8 +18,12 @@ from ffsim_b200.gates.orbital_rotation import _rotate_device
 from ffsim_b200.states import dim
 
 
-def axpby(alpha: complex, x: torch.Tensor, beta: complex, y: torch.Tensor) -> None:
-    """y = alpha * x + beta * y on the device."""
+def axpby(alpha: complex, x, beta: complex, y) -> None:
+    """y = alpha * x + beta * y on the device (tensors or ShardedVectors)."""
+    if _device.is_sharded(x):
+        x, y = x.local, y.local
+    if x.numel() == 0:
+        return
     with torch.cuda.device(x.device):
         _device.sync_device()
         _lib.check(
@@ -52,11 +56,11 @@ class DiagonalCoulombHamiltonian:
         )
         constant = self.constant
 
-        def matvec(t: torch.Tensor) -> torch.Tensor:
+        def matvec(t):
             # num_linop @ vec: rotate into the eigenbasis of h, contract, rotate back
             work = t.clone()
             _rotate_device(work, vecs_dag, vecs_dag, norb, nelec)
-            result = torch.empty_like(t)
+            result = _device.empty_like(t)
             _contract_num(work, result, eigs, norb, nelec, accumulate=False)
             _rotate_device(result, vecs, vecs, norb, nelec)
             # + dc_linop @ vec (accumulate form) + constant * vec

@@ -11,6 +11,7 @@ import numpy as np
 import scipy.linalg
 import torch
 
+from ffsim_b200 import _device
 from ffsim_b200.contract.diag_coulomb import _contract_device as _contract_dc
 from ffsim_b200.contract.diag_coulomb import _get_mats
 from ffsim_b200.contract.linop import DeviceLinearOperator
@@ -47,13 +48,13 @@ class DoubleFactorizedHamiltonian:
         ]
         constant, z_rep = self.constant, self.z_representation
 
-        def matvec(t: torch.Tensor) -> torch.Tensor:
+        def matvec(t):
             work = t.clone()
             _rotate_device(work, vecs_dag, vecs_dag, norb, nelec)
-            result = torch.empty_like(t)
+            result = _device.empty_like(t)
             _contract_num(work, result, eigs, norb, nelec, accumulate=False)
             _rotate_device(result, vecs, vecs, norb, nelec)
-            tmp = torch.empty_like(t)
+            tmp = _device.empty_like(t)
             for mats, rot in terms:
                 work.copy_(t)
                 rot_dag = rot.T.conj()

@@ -141,6 +141,15 @@ int ffb_apply_orbital_rotation(ffb_plan *p, void *vec_dev, void *workspace_dev, 
  * other index).  side: 0 = alpha rotations of the plan, 1 = beta rotations. */
 int ffb_apply_orbital_rotation_rows(ffb_plan *p, int side, void *mat_dev, int64_t n_cols, int64_t ld,
                                     void *stream);
+/* The same with general strides: element (string address r, batch index c) lives at
+ * data[r * row_stride + c * col_stride].  With row_stride = 1 and col_stride = dim_b this
+ * rotates the beta (contiguous) index of n_batch locally held alpha rows in place, without a
+ * transposed copy; the kernel then stages whole rows and is efficient when the beta sector
+ * fits one shared-memory window (ffb_plan_beta_in_place != 0). */
+int ffb_apply_orbital_rotation_strided(ffb_plan *p, int side, void *data_dev, int64_t n_batch,
+                                       int64_t row_stride, int64_t col_stride, void *stream);
+/* 1 when the plan rotates the beta index in place, 0 when it goes through a transposed copy. */
+int ffb_plan_beta_in_place(const ffb_plan *p);
 
 /* ------------------------------------------------------ diagonal operators
  * Replaces src/gates/diag_coulomb.rs:21,95 (num / z representation),

@@ -1,0 +1,122 @@
+"""Row-sharded LUCJ / DC-Hamiltonian-energy benchmark (torchrun, one rank per GPU).
+
+    torchrun --nproc-per-node N scripts/bench_sharded.py --norb 20 --nelec 8 8 --n-reps 3
+
+Times apply_unitary(UCJOpSpinBalanced) on a sharded Hartree-Fock state (BASELINE config C4) and
+optionally the DiagonalCoulombHamiltonian energy (C5), device-timed, max over ranks; reports the
+per-rank HBM and NVLink volumes and the parity of the first rotation against Slater minors.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import ffsim_b200 as ffsim
+from ffsim_b200 import distributed
+from ffsim_b200.distributed import ShardedVector
+
+
+def slater_minors(u, norb, nocc):
+    """det U[I, :nocc] for every string I (ascending): the closed form of U|HF> (python/ffsim/states/slater.py:303-354)."""
+    occ = ffsim.cistring.gen_occslst(norb, nocc).astype(np.int64)
+    sub = u[occ[:, :, None], np.arange(nocc)[None, None, :]]
+    out = np.empty(len(occ), dtype=complex)
+    step = 20000
+    for i in range(0, len(occ), step):
+        out[i:i + step] = np.linalg.det(sub[i:i + step])
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--norb", type=int, default=14)
+    ap.add_argument("--nelec", type=int, nargs=2, default=[6, 6])
+    ap.add_argument("--n-reps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--energy", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    norb, nelec = args.norb, tuple(args.nelec)
+    ffsim.init_cache(norb, nelec)
+    pairs_aa = [(p, p + 1) for p in range(norb - 1)]
+    pairs_ab = [(p, p) for p in range(norb)]
+    op = ffsim.random.random_ucj_op_spin_balanced(norb, n_reps=args.n_reps, interaction_pairs=(pairs_aa, pairs_ab),
+                                                  seed=2004)
+    dim = ffsim.dim(norb, nelec)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # parity of one sharded rotation against the closed form (outer product of Slater minors)
+    hf = ShardedVector.hartree_fock(norb, nelec, device=dev)
+    u = op.orbital_rotations[0]
+    rot = ffsim.apply_orbital_rotation(hf, u, norb, nelec, copy=False)
+    ma, mb = slater_minors(u, norb, nelec[0]), slater_minors(u, norb, nelec[1])
+    want_local = torch.from_numpy(np.outer(ma[rot.row0:rot.row0 + rot.n_rows], mb).reshape(-1)).to(dev)
+    num = torch.linalg.vector_norm(rot.local - want_local) ** 2
+    acc = torch.stack([num, torch.linalg.vector_norm(want_local) ** 2])
+    if world > 1:
+        dist.all_reduce(acc)
+    parity = float(torch.sqrt(acc[0] / acc[1]))
+    del want_local, rot
+
+    times = []
+    state = ShardedVector.hartree_fock(norb, nelec, device=dev)
+    for it in range(args.steps + 1):
+        state.local.zero_()
+        if state.row0 == 0:
+            state.local[0] = 1
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        state = ffsim.apply_unitary(state, op, norb=norb, nelec=nelec, copy=False)
+        b.record()
+        sync()
+        t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it > 0:
+            times.append(float(t))
+    norm = state.norm()
+    out = {"workload": f"LUCJ n_reps={args.n_reps} on Hartree-Fock, norb={norb} nelec={list(nelec)}, row-sharded",
+           "n_gpus": world, "dim": dim, "state_GB": dim * 16 / 1e9, "ms": float(np.median(times)),
+           "applications_per_s": 1e3 / float(np.median(times)), "norm": norm,
+           "rotation_parity_vs_slater_minors": parity,
+           "all_to_all_per_rotation": 2, "nvlink_bytes_per_rank_per_all_to_all": distributed.all_to_all_bytes(state),
+           "algorithmic_hbm_bytes_total": ((args.n_reps + 1) * 64 + args.n_reps * 32) * dim}
+    n_a2a = 2 * (args.n_reps + 1)
+    out["nvlink_GBps_if_comm_bound"] = n_a2a * out["nvlink_bytes_per_rank_per_all_to_all"] / (out["ms"] * 1e-3) / 1e9
+    out["algorithmic_TBps_total"] = out["algorithmic_hbm_bytes_total"] / (out["ms"] * 1e-3) / 1e12
+    if args.energy:
+        ham = ffsim.random.random_diagonal_coulomb_hamiltonian(norb, seed=2405)
+        linop = ffsim.linear_operator(ham, norb=norb, nelec=nelec)
+        sync()
+        t0 = time.perf_counter()
+        hv = linop @ state
+        energy = state.vdot(hv).real
+        sync()
+        out["energy_ms"] = (time.perf_counter() - t0) * 1e3
+        out["energy"] = energy
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
