@@ -1,0 +1,231 @@
+"""Generate tests/golden/ref_*.npz by running the REFERENCE's own Python code (see ref_shim.py).
+
+    python tests/golden/make_golden.py          # in the build container only
+
+Every case is produced by the reference's public drivers (python/ffsim/gates/*.py,
+contract/*.py, variational/ucj_spin_balanced.py, trotter/*.py, hamiltonians/*.py) with
+inputs from the reference's own generators (python/ffsim/random/random.py), executing the
+reference's pure-Python kernel twins (python/ffsim/_slow/**).  Inputs and outputs are both
+stored, so the tests do not depend on any generator of this repository.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+import ffsim.random.random as rr  # noqa: E402
+from ffsim.contract.diag_coulomb import contract_diag_coulomb  # noqa: E402
+from ffsim.contract.num_op_sum import contract_num_op_sum  # noqa: E402
+from ffsim.gates.diag_coulomb import apply_diag_coulomb_evolution  # noqa: E402
+from ffsim.gates.num_op_sum import apply_num_op_sum_evolution  # noqa: E402
+from ffsim.gates.orbital_rotation import (  # noqa: E402
+    _one_subspace_indices,
+    _zero_one_subspace_indices,
+    apply_orbital_rotation,
+)
+from ffsim.hamiltonians.diagonal_coulomb_hamiltonian import DiagonalCoulombHamiltonian  # noqa: E402
+from ffsim.protocols.apply_unitary_protocol import apply_unitary  # noqa: E402
+from ffsim.protocols.linear_operator_protocol import linear_operator  # noqa: E402
+from ffsim.states.dimensions import dim as ref_dim  # noqa: E402
+from ffsim.states.slater import hartree_fock_state  # noqa: E402
+from ffsim.trotter.diagonal_coulomb_split_op import simulate_trotter_diag_coulomb_split_op  # noqa: E402
+from ffsim.trotter.double_factorized import simulate_trotter_double_factorized  # noqa: E402
+
+CASES: dict[str, dict] = {}
+NONE = np.zeros((0,))  # stands for a `None` member
+
+
+def opt(x):
+    return NONE if x is None else np.asarray(x)
+
+
+def add(name, **arrays):
+    assert name not in CASES, name
+    CASES[name] = {k: np.asarray(v) for k, v in arrays.items()}
+
+
+def main():
+    # ---- generators (pins oracle/rand.py and ffsim_b200/random.py) ----
+    add("random/unitary_5_seed11", kind="random_unitary", n=5, seed=11, expected=rr.random_unitary(5, seed=11))
+    add("random/real_symmetric_6_seed12", kind="random_real_symmetric_matrix", n=6, seed=12,
+        expected=rr.random_real_symmetric_matrix(6, seed=12))
+    add("random/state_vector_20_seed13", kind="random_state_vector", n=20, seed=13,
+        expected=rr.random_state_vector(20, seed=13))
+
+    # ---- address tables (reference argsort construction, orbital_rotation.py:203-236) ----
+    for norb, nocc in [(4, 2), (6, 3), (7, 2), (8, 5)]:
+        for (i, j) in sorted({(0, 1), (1, 0), (norb - 2, norb - 1), (2, 3), (3, 2)}):
+            add(f"tables/zero_one_{norb}_{nocc}_{i}_{j}", kind="zero_one", norb=norb, nocc=nocc, i=i, j=j,
+                expected=_zero_one_subspace_indices(norb, nocc, (i, j)).astype(np.int64))
+        add(f"tables/one_{norb}_{nocc}", kind="one", norb=norb, nocc=nocc, i=1,
+            expected=_one_subspace_indices(norb, nocc, (1,)).astype(np.int64))
+
+    # ---- orbital rotation ----
+    rng = np.random.default_rng(20261017)
+    for norb, nelec in [(4, (2, 2)), (5, (3, 2)), (6, (3, 3)), (6, (1, 4)), (3, (0, 2)), (7, (3, 2))]:
+        d = ref_dim(norb, nelec)
+        vec = rr.random_state_vector(d, seed=rng)
+        ua, ub = rr.random_unitary(norb, seed=rng), rr.random_unitary(norb, seed=rng)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}"
+        add(f"orbital_rotation/same_{tag}", kind="orbital_rotation", norb=norb, nelec=nelec, vec=vec,
+            mat_a=ua, mat_b=ua, expected=apply_orbital_rotation(vec, ua, norb, nelec))
+        add(f"orbital_rotation/pair_{tag}", kind="orbital_rotation", norb=norb, nelec=nelec, vec=vec,
+            mat_a=ua, mat_b=ub, expected=apply_orbital_rotation(vec, (ua, ub), norb, nelec))
+        add(f"orbital_rotation/alpha_only_{tag}", kind="orbital_rotation", norb=norb, nelec=nelec, vec=vec,
+            mat_a=ua, mat_b=NONE, expected=apply_orbital_rotation(vec, (ua, None), norb, nelec))
+        add(f"orbital_rotation/beta_only_{tag}", kind="orbital_rotation", norb=norb, nelec=nelec, vec=vec,
+            mat_a=NONE, mat_b=ub, expected=apply_orbital_rotation(vec, (None, ub), norb, nelec))
+    for norb, nocc in [(5, 3), (6, 2)]:
+        d = ref_dim(norb, nocc)
+        vec = rr.random_state_vector(d, seed=rng)
+        u = rr.random_unitary(norb, seed=rng)
+        add(f"orbital_rotation/spinless_{norb}_{nocc}", kind="orbital_rotation_spinless", norb=norb, nelec=nocc,
+            vec=vec, mat_a=u, expected=apply_orbital_rotation(vec, u, norb, nocc))
+    # one mid-size case: several tiles / register-block classes on the CUDA side
+    norb, nelec = 9, (4, 3)
+    vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng)
+    ua, ub = rr.random_unitary(norb, seed=rng), rr.random_unitary(norb, seed=rng)
+    add("orbital_rotation/pair_9_4_3", kind="orbital_rotation", norb=norb, nelec=nelec, vec=vec,
+        mat_a=ua, mat_b=ub, expected=apply_orbital_rotation(vec, (ua, ub), norb, nelec))
+    # a permutation matrix and the identity: rotations that degenerate (c = 0 / no rotations)
+    norb, nelec = 5, (2, 3)
+    vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng)
+    perm = np.eye(norb)[:, [2, 0, 4, 1, 3]].astype(complex)
+    add("orbital_rotation/permutation_5_2_3", kind="orbital_rotation", norb=norb, nelec=nelec, vec=vec,
+        mat_a=perm, mat_b=perm, expected=apply_orbital_rotation(vec, perm, norb, nelec))
+    add("orbital_rotation/identity_5_2_3", kind="orbital_rotation", norb=norb, nelec=nelec, vec=vec,
+        mat_a=np.eye(norb, dtype=complex), mat_b=np.eye(norb, dtype=complex),
+        expected=apply_orbital_rotation(vec, np.eye(norb, dtype=complex), norb, nelec))
+
+    # ---- diagonal Coulomb evolution ----
+    for norb, nelec in [(4, (2, 2)), (5, (3, 2)), (6, (2, 3))]:
+        d = ref_dim(norb, nelec)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}"
+        vec = rr.random_state_vector(d, seed=rng)
+        u = rr.random_unitary(norb, seed=rng)
+        maa = rr.random_real_symmetric_matrix(norb, seed=rng)
+        mab = rng.standard_normal((norb, norb))  # alpha-beta block need not be symmetric
+        mbb = rr.random_real_symmetric_matrix(norb, seed=rng)
+        t = 0.73
+        for z in (False, True):
+            zt = "z" if z else "num"
+            add(f"diag_coulomb/sym_{zt}_{tag}", kind="diag_coulomb", norb=norb, nelec=nelec, vec=vec, time=t, z=z,
+                mat_aa=maa, mat_ab=maa, mat_bb=maa, rot=NONE, single=1,
+                expected=apply_diag_coulomb_evolution(vec, maa, t, norb, nelec, z_representation=z))
+            add(f"diag_coulomb/triple_{zt}_{tag}", kind="diag_coulomb", norb=norb, nelec=nelec, vec=vec, time=t, z=z,
+                mat_aa=maa, mat_ab=mab, mat_bb=mbb, rot=NONE, single=0,
+                expected=apply_diag_coulomb_evolution(vec, (maa, mab, mbb), t, norb, nelec, z_representation=z))
+            add(f"diag_coulomb/ab_only_{zt}_{tag}", kind="diag_coulomb", norb=norb, nelec=nelec, vec=vec, time=t, z=z,
+                mat_aa=NONE, mat_ab=mab, mat_bb=NONE, rot=NONE, single=0,
+                expected=apply_diag_coulomb_evolution(vec, (None, mab, None), t, norb, nelec, z_representation=z))
+            add(f"diag_coulomb/rotated_{zt}_{tag}", kind="diag_coulomb", norb=norb, nelec=nelec, vec=vec, time=t, z=z,
+                mat_aa=maa, mat_ab=mab, mat_bb=mbb, rot=u, single=0,
+                expected=apply_diag_coulomb_evolution(vec, (maa, mab, mbb), t, norb, nelec, orbital_rotation=u,
+                                                      z_representation=z))
+    norb, nocc = 5, 2
+    vec = rr.random_state_vector(ref_dim(norb, nocc), seed=rng)
+    m = rr.random_real_symmetric_matrix(norb, seed=rng)
+    add("diag_coulomb/spinless_5_2", kind="diag_coulomb_spinless", norb=norb, nelec=nocc, vec=vec, time=0.4,
+        mat_aa=m, expected=apply_diag_coulomb_evolution(vec, m, 0.4, norb, nocc))
+
+    # ---- number-operator-sum evolution ----
+    for norb, nelec in [(4, (2, 2)), (6, (3, 2))]:
+        d = ref_dim(norb, nelec)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}"
+        vec = rr.random_state_vector(d, seed=rng)
+        u = rr.random_unitary(norb, seed=rng)
+        ca, cb = rng.standard_normal(norb), rng.standard_normal(norb)
+        t = 1.3
+        add(f"num_op_sum/same_{tag}", kind="num_op_sum", norb=norb, nelec=nelec, vec=vec, time=t,
+            coeffs_a=ca, coeffs_b=ca, rot=NONE, expected=apply_num_op_sum_evolution(vec, ca, t, norb, nelec))
+        add(f"num_op_sum/pair_{tag}", kind="num_op_sum", norb=norb, nelec=nelec, vec=vec, time=t,
+            coeffs_a=ca, coeffs_b=cb, rot=NONE, expected=apply_num_op_sum_evolution(vec, (ca, cb), t, norb, nelec))
+        add(f"num_op_sum/beta_only_{tag}", kind="num_op_sum", norb=norb, nelec=nelec, vec=vec, time=t,
+            coeffs_a=NONE, coeffs_b=cb, rot=NONE,
+            expected=apply_num_op_sum_evolution(vec, (None, cb), t, norb, nelec))
+        add(f"num_op_sum/rotated_{tag}", kind="num_op_sum", norb=norb, nelec=nelec, vec=vec, time=t,
+            coeffs_a=ca, coeffs_b=cb, rot=u,
+            expected=apply_num_op_sum_evolution(vec, (ca, cb), t, norb, nelec, orbital_rotation=u))
+
+    # ---- contractions ----
+    for norb, nelec in [(4, (2, 2)), (5, (2, 3))]:
+        d = ref_dim(norb, nelec)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}"
+        vec = rr.random_state_vector(d, seed=rng)
+        maa = rr.random_real_symmetric_matrix(norb, seed=rng)
+        mab = rng.standard_normal((norb, norb))
+        mbb = rr.random_real_symmetric_matrix(norb, seed=rng)
+        ca, cb = rng.standard_normal(norb), rng.standard_normal(norb)
+        for z in (False, True):
+            zt = "z" if z else "num"
+            add(f"contract_diag_coulomb/sym_{zt}_{tag}", kind="contract_diag_coulomb", norb=norb, nelec=nelec,
+                vec=vec, z=z, mat_aa=maa, mat_ab=maa, mat_bb=maa, single=1,
+                expected=contract_diag_coulomb(vec, maa, norb, nelec, z_representation=z))
+            add(f"contract_diag_coulomb/triple_{zt}_{tag}", kind="contract_diag_coulomb", norb=norb, nelec=nelec,
+                vec=vec, z=z, mat_aa=maa, mat_ab=mab, mat_bb=mbb, single=0,
+                expected=contract_diag_coulomb(vec, (maa, mab, mbb), norb, nelec, z_representation=z))
+        add(f"contract_num_op_sum/same_{tag}", kind="contract_num_op_sum", norb=norb, nelec=nelec, vec=vec,
+            coeffs_a=ca, coeffs_b=ca, expected=contract_num_op_sum(vec, ca, norb, nelec))
+
+    # ---- UCJOpSpinBalanced / LUCJ (variational/ucj_spin_balanced.py:657) ----
+    for norb, nelec, n_reps, final, lucj in [(4, (2, 2), 2, True, True), (5, (3, 2), 3, False, False),
+                                            (6, (3, 3), 2, True, True), (8, (4, 4), 2, True, True)]:
+        pairs = None
+        if lucj:  # docs/explanations/lucj.ipynb:392-393
+            pairs = ([(p, p + 1) for p in range(norb - 1)], [(p, p) for p in range(norb)])
+        op = rr.random_ucj_op_spin_balanced(norb, n_reps=n_reps, interaction_pairs=pairs,
+                                            with_final_orbital_rotation=final, seed=rng)
+        vec = hartree_fock_state(norb, nelec)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}_L{n_reps}"
+        add(f"ucj/{'lucj' if lucj else 'full'}_{tag}", kind="ucj", norb=norb, nelec=nelec, vec=vec,
+            diag_coulomb_mats=op.diag_coulomb_mats, orbital_rotations=op.orbital_rotations,
+            final_orbital_rotation=opt(op.final_orbital_rotation),
+            expected=apply_unitary(vec, op, norb=norb, nelec=nelec))
+
+    # ---- double-factorized Trotter (trotter/double_factorized.py:25) ----
+    for norb, nelec, rank, z, order, n_steps in [(4, (2, 2), 3, False, 0, 1), (4, (2, 2), 3, False, 1, 2),
+                                                 (5, (2, 3), 4, True, 0, 2), (4, (1, 2), 2, False, 2, 1)]:
+        ham = rr.random_double_factorized_hamiltonian(norb, rank=rank, z_representation=z, seed=rng)
+        vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng)
+        t = 0.35
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}_r{rank}_{'z' if z else 'num'}_o{order}_s{n_steps}"
+        add(f"trotter_df/{tag}", kind="trotter_df", norb=norb, nelec=nelec, vec=vec, time=t, order=order,
+            n_steps=n_steps, z=z, one_body_tensor=ham.one_body_tensor, diag_coulomb_mats=ham.diag_coulomb_mats,
+            orbital_rotations=ham.orbital_rotations, constant=ham.constant,
+            expected=simulate_trotter_double_factorized(vec, ham, t, norb=norb, nelec=nelec, n_steps=n_steps,
+                                                        order=order))
+
+    # ---- DiagonalCoulombHamiltonian: matvec and split-operator Trotter ----
+    for norb, nelec in [(4, (2, 2)), (5, (3, 2))]:
+        ham = rr.random_diagonal_coulomb_hamiltonian(norb, seed=rng)
+        vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}"
+        lin = linear_operator(ham, norb=norb, nelec=nelec)
+        add(f"dc_hamiltonian/matvec_{tag}", kind="dc_matvec", norb=norb, nelec=nelec, vec=vec,
+            one_body_tensor=ham.one_body_tensor, diag_coulomb_mats=ham.diag_coulomb_mats, constant=ham.constant,
+            expected=lin @ vec)
+        add(f"dc_hamiltonian/split_op_{tag}", kind="dc_split_op", norb=norb, nelec=nelec, vec=vec, time=0.2,
+            order=1, n_steps=2, one_body_tensor=ham.one_body_tensor, diag_coulomb_mats=ham.diag_coulomb_mats,
+            constant=ham.constant,
+            expected=simulate_trotter_diag_coulomb_split_op(vec, ham, 0.2, norb=norb, nelec=nelec, n_steps=2, order=1))
+
+    flat = {}
+    for name, arrays in CASES.items():
+        for k, v in arrays.items():
+            flat[f"{name}::{k}"] = v
+    out = os.path.join(HERE, "reference_vectors.npz")
+    np.savez_compressed(out, **flat)
+    print(f"wrote {len(CASES)} cases, {os.path.getsize(out) / 1024:.1f} KiB -> {out}")
+
+
+if __name__ == "__main__":
+    main()
