@@ -340,6 +340,18 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
       P.rsr[r] = nr.s.real();
       P.rsi[r] = nr.s.imag();
     }
+    // dispatch units: descending runs inside each sub-pass
+    int n_run = 0;
+    for (int s = 0; s < P.n_sub; ++s) {
+      const SubPass &sub = dp.sched.subs[s];
+      P.sub[s].run_begin = (unsigned short)n_run;
+      for (const Run &run : segment_runs(P.rq, sub.rot_begin, sub.rot_end, sub.q0)) {
+        P.runcode[n_run] = (unsigned char)run_code(run.q_hi_rel, run.len);
+        P.runrot[n_run] = (unsigned short)run.first;
+        ++n_run;
+      }
+      P.sub[s].run_end = (unsigned short)n_run;
+    }
     int ng = 0;
     long long units = 0;
     size_t tile_bytes = 0;
@@ -377,11 +389,9 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     P.n_groups = ng;
     P.total_units = units;
     if (units == 0) continue;
-    int grid = (int)std::min<long long>(units, plan->dev.sm_count);
-    // small tiles: let several CTAs share an SM
-    size_t per_cta = tile_bytes + overhead + 1024;
-    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, plan->dev.smem_optin / per_cta));
-    grid = (int)std::min<long long>(units, (long long)plan->dev.sm_count * ctas_per_sm);
+    // persistent grid: every CTA resident at once (registers, shared memory and threads counted)
+    const int ctas_per_sm = fused_pass_ctas_per_sm(P.w, plan->opt.threads, tile_bytes);
+    const int grid = (int)std::min<long long>(units, (long long)plan->dev.sm_count * ctas_per_sm);
     {
       ProfScope prof(kProfFused, 32.0 * (double)dim * (double)n_cols, stream);
       FFB_CUDA(launch_fused_pass(P, grid, plan->opt.threads, tile_bytes, stream));

@@ -2,6 +2,12 @@
 #pragma once
 #include <stdint.h>
 
+#ifdef __CUDACC__
+#define FFB_HD __host__ __device__
+#else
+#define FFB_HD
+#endif
+
 namespace ffb {
 
 constexpr int kMaxGroups = 33;       // distinct electron counts inside a window
@@ -40,7 +46,14 @@ struct SubMeta {
   unsigned char q0;
   unsigned char pad;
   unsigned short rot_begin, rot_end;
+  unsigned short run_begin, run_end;  // dispatch units of the sub-pass (see PassParams::runcode)
 };
+
+// A run is up to kMaxRunLen consecutive rotations of a sub-pass whose pair positions descend by
+// one (q, q-1, ...): the shape the Givens decomposition emits.  The kernel dispatches once per
+// run to straight-line code for all of its rotations.
+constexpr int kMaxRunLen = 3;
+FFB_HD constexpr int run_code(int q_hi_rel, int len) { return q_hi_rel * 4 + len; }
 
 struct PassParams {
   void *data;  // complex128 state (or transposed workspace), updated in place
@@ -59,6 +72,10 @@ struct PassParams {
   // rotation r of the pass: pair position relative to the pass window and (c, s);
   // one spare slot so that the kernel may prefetch entry r + 1
   unsigned char rq[kMaxRotPerPass + 8];
+  // run k of the pass: run_code(position of its first rotation relative to the sub-window, length)
+  // and the index of its first rotation
+  unsigned char runcode[kMaxRotPerPass + 8];
+  unsigned short runrot[kMaxRotPerPass + 8];
   double rc[kMaxRotPerPass + 1], rsr[kMaxRotPerPass + 1], rsi[kMaxRotPerPass + 1];
 };
 

@@ -81,22 +81,49 @@ __device__ __forceinline__ void rot_block(double2 (&a)[cbinom(W, M)], double c, 
   }
 }
 
-template <int W, int M, int Q = 0>
-__device__ __forceinline__ void rot_dispatch(double2 (&a)[cbinom(W, M)], int q, double c,
-                                             double sr, double si) {
-  if constexpr (Q < W - 1) {
-    if (q == Q)
-      rot_block<W, M, Q>(a, c, sr, si);
-    else
-      rot_dispatch<W, M, Q + 1>(a, q, c, sr, si);
+// A run of LEN rotations on block-relative pairs (QHI, QHI+1), (QHI-1, QHI), ...: straight-line
+// code, coefficients read from the constant bank (the pass parameters).
+template <int W, int M, int QHI, int LEN>
+__device__ __forceinline__ void run_block(double2 (&a)[cbinom(W, M)], const PassParams &p, int r) {
+  if constexpr (QHI <= W - 2 && QHI - LEN + 1 >= 0) {
+    double c[LEN], sr[LEN], si[LEN];
+#pragma unroll
+    for (int i = 0; i < LEN; ++i) {
+      c[i] = p.rc[r + i];
+      sr[i] = p.rsr[r + i];
+      si[i] = p.rsi[r + i];
+    }
+    if constexpr (LEN >= 1) rot_block<W, M, QHI>(a, c[0], sr[0], si[0]);
+    if constexpr (LEN >= 2) rot_block<W, M, QHI - 1>(a, c[1], sr[1], si[1]);
+    if constexpr (LEN >= 3) rot_block<W, M, QHI - 2>(a, c[2], sr[2], si[2]);
   }
 }
+
+#define FFB_RUN_CASE(QHI, LEN) \
+  case run_code(QHI, LEN):     \
+    run_block<W, M, QHI, LEN>(a, p, r); \
+    break;
+
+template <int W, int M>
+__device__ __forceinline__ void run_dispatch(double2 (&a)[cbinom(W, M)], const PassParams &p, int code,
+                                             int r) {
+  static_assert(kMaxRunLen == 3, "run_dispatch enumerates run lengths 1..3");
+  switch (code) {
+    FFB_RUN_CASE(0, 1)
+    FFB_RUN_CASE(1, 1) FFB_RUN_CASE(1, 2)
+    FFB_RUN_CASE(2, 1) FFB_RUN_CASE(2, 2) FFB_RUN_CASE(2, 3)
+    FFB_RUN_CASE(3, 1) FFB_RUN_CASE(3, 2) FFB_RUN_CASE(3, 3)
+    FFB_RUN_CASE(4, 1) FFB_RUN_CASE(4, 2) FFB_RUN_CASE(4, 3)
+    default: break;
+  }
+}
+#undef FFB_RUN_CASE
 
 // One register block: gather, rotate, scatter.
 template <int W, int M>
 __device__ __forceinline__ void process_item(double2 *__restrict__ tile, int cols, int col,
                                              uint32_t entry, const uint16_t *__restrict__ offtab,
-                                             const PassParams &p, int r0, int r1, int q0) {
+                                             const PassParams &p, int run0, int run1) {
   constexpr int N = cbinom(W, M);
   const int base = (int)(entry & 0xFFFFFFu);
   const uint16_t *o = offtab + (entry >> 24) * kOffRow + cclass_offset(W, M);
@@ -111,18 +138,13 @@ __device__ __forceinline__ void process_item(double2 *__restrict__ tile, int col
     else
       idx2[t >> 1] = i;
   }
-  // software-pipelined coefficient fetch: the next rotation's (q, c, s) is loaded from the
-  // constant bank while the current one is applied (the arrays have a spare slot at the end)
-  int q = (int)p.rq[r0] - q0;
-  double c = p.rc[r0], sr = p.rsr[r0], si = p.rsi[r0];
-  for (int r = r0; r < (FFB_KNOB(4) ? r0 : r1); ++r) {
-    const int qn = (int)p.rq[r + 1] - q0;
-    const double cn = p.rc[r + 1], srn = p.rsr[r + 1], sin_ = p.rsi[r + 1];
-    rot_dispatch<W, M>(a, q, c, sr, si);
-    q = qn;
-    c = cn;
-    sr = srn;
-    si = sin_;
+  // one dispatch per run; the next run's descriptor is fetched while the current one executes
+  int code = p.runcode[run0], r = p.runrot[run0];
+  for (int run = run0; run < (FFB_KNOB(4) ? run0 : run1); ++run) {
+    const int code_n = p.runcode[run + 1], r_n = p.runrot[run + 1];
+    run_dispatch<W, M>(a, p, code, r);
+    code = code_n;
+    r = r_n;
   }
 #pragma unroll
   for (int t = 0; t < N; ++t) tile[(t & 1) ? (idx2[t >> 1] >> 16) : (idx2[t >> 1] & 0xFFFFu)] = a[t];
@@ -131,12 +153,12 @@ __device__ __forceinline__ void process_item(double2 *__restrict__ tile, int col
 template <int W, int M = 1>
 __device__ __forceinline__ void process_dispatch(int mp, double2 *tile, int cols, int col,
                                                  uint32_t entry, const uint16_t *offtab,
-                                                 const PassParams &p, int r0, int r1, int q0) {
+                                                 const PassParams &p, int run0, int run1) {
   if constexpr (M < W) {
     if (mp == M)
-      process_item<W, M>(tile, cols, col, entry, offtab, p, r0, r1, q0);
+      process_item<W, M>(tile, cols, col, entry, offtab, p, run0, run1);
     else
-      process_dispatch<W, M + 1>(mp, tile, cols, col, entry, offtab, p, r0, r1, q0);
+      process_dispatch<W, M + 1>(mp, tile, cols, col, entry, offtab, p, run0, run1);
   }
 }
 
@@ -289,7 +311,7 @@ __global__ void __launch_bounds__(512, 1)
           for (int e = tid; e < kOffTabEntries / 8; e += nthr) cp_async16(dst + 8 * e, src + 8 * e);
         }
         const GroupSubDev &gs = gsub_s[s];
-        const int q0 = p.sub[s].q0, r0 = p.sub[s].rot_begin, r1 = p.sub[s].rot_end;
+        const int run0 = p.sub[s].run_begin, run1 = p.sub[s].run_end;
         const int n_chunks = total_chunks(gs, cols);
         // chunks 0..nwarp-1 are owned statically (their descriptors were prefetched before the
         // previous barrier); the rest are handed out dynamically, heaviest first
@@ -314,7 +336,7 @@ __global__ void __launch_bounds__(512, 1)
             nxt.col = 0;
           }
           if (have && cur.mp && !FFB_KNOB(8))
-            process_dispatch<W>(cur.mp, tile, cols, cur.col, cur.entry, offtab, p, r0, r1, q0);
+            process_dispatch<W>(cur.mp, tile, cols, cur.col, cur.entry, offtab, p, run0, run1);
           cur = nxt;
           if (g_next >= n_chunks) break;
           g = g_next;
@@ -369,6 +391,31 @@ static cudaError_t launch_w(const PassParams &p, int grid, int threads, size_t s
 }
 
 size_t fused_pass_smem_overhead() { return kFusedSmemOverhead; }
+
+template <int W>
+static int occupancy_w(int threads, size_t smem) {
+  int n = 0;
+  cudaFuncSetAttribute(fused_pass_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_pass_kernel<W>, threads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 1;
+  }
+  return n < 1 ? 1 : n;
+}
+
+// CTAs of the fused kernel that are resident on one SM at this block size and tile size
+// (registers, shared memory and thread limits all counted).
+int fused_pass_ctas_per_sm(int w, int threads, size_t tile_bytes) {
+  const size_t smem = tile_bytes + fused_pass_smem_overhead();
+  switch (w) {
+    case 2: return occupancy_w<2>(threads, smem);
+    case 3: return occupancy_w<3>(threads, smem);
+    case 4: return occupancy_w<4>(threads, smem);
+    case 5: return occupancy_w<5>(threads, smem);
+    case 6: return occupancy_w<6>(threads, smem);
+    default: return 1;
+  }
+}
 
 #ifdef FFB_DEBUG_KNOBS
 void set_debug_knobs(int v) { cudaMemcpyToSymbol(g_debug_knobs, &v, sizeof(int)); }

@@ -103,6 +103,16 @@ struct PassTablesHost {
 };
 PassTablesHost build_pass_tables(int norb, int nocc, const PassSchedule &pass);
 
+// Dispatch units of a sub-pass: maximal runs (length <= kMaxRunLen) of consecutive rotations
+// whose pair positions descend by one.  rq[] holds positions relative to the pass window;
+// q_hi_rel is relative to the sub-window start q0.
+struct Run {
+  int first;     // index of the first rotation (into the pass's rotation arrays)
+  int len;
+  int q_hi_rel;  // position of the first rotation's pair inside the register block
+};
+std::vector<Run> segment_runs(const unsigned char *rq, int rot_begin, int rot_end, int q0);
+
 // start of the m' class inside a row of `off`: sum_{1 <= j < m'} C(w, j)
 int class_offset(int w, int mprime);
 

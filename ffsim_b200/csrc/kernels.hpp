@@ -12,6 +12,7 @@ struct PhaseList {  // per-orbital phases passed by value
 };
 
 size_t fused_pass_smem_overhead();
+int fused_pass_ctas_per_sm(int w, int threads, size_t tile_bytes);
 cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t tile_bytes,
                               cudaStream_t stream);
 cudaError_t launch_givens_single(void *vec, long long ld, long long dim_b, double c, double sr,

@@ -184,6 +184,20 @@ SideSchedule build_schedule(int norb, int nocc, const std::vector<int> &q, const
   return sched;
 }
 
+std::vector<Run> segment_runs(const unsigned char *rq, int rot_begin, int rot_end, int q0) {
+  std::vector<Run> runs;
+  int r = rot_begin;
+  while (r < rot_end) {
+    Run run{r, 1, (int)rq[r] - q0};
+    while (run.len < kMaxRunLen && r + run.len < rot_end &&
+           (int)rq[r + run.len] == (int)rq[r] - run.len)
+      ++run.len;
+    runs.push_back(run);
+    r += run.len;
+  }
+  return runs;
+}
+
 // sum over the set bits of `pattern` (ascending) of C(shift + pos, first_index + i)
 static uint64_t placed_rank(uint64_t pattern, int shift, int first_index) {
   uint64_t r = 0;

@@ -7,6 +7,7 @@
 // suite validate the schedule and every index table without a GPU; it is not a
 // product path and nothing in ffsim_b200/ can reach it.
 #include <complex>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -96,6 +97,22 @@ extern "C" int ffb_hostcheck_apply_side(int norb, int nocc, const ffb_givens_rot
     }
     for (int64_t r = 0; r < dim; ++r)
       if (!row_seen[r]) return -103;
+    // dispatch runs: partition each sub-pass's rotations into descending runs the kernel has code for
+    {
+      std::vector<unsigned char> rq(ps.rot_index.size() + 8, 0);
+      for (size_t r = 0; r < ps.rot_index.size(); ++r) rq[r] = (unsigned char)(nr[ps.rot_index[r]].q - ps.lo);
+      for (const SubPass &sp : ps.subs) {
+        int expect = sp.rot_begin;
+        for (const Run &run : segment_runs(rq.data(), sp.rot_begin, sp.rot_end, sp.q0)) {
+          if (run.first != expect || run.len < 1 || run.len > kMaxRunLen) return -106;
+          if (run.q_hi_rel > sp.w - 2 || run.q_hi_rel - run.len + 1 < 0) return -107;
+          for (int i = 0; i < run.len; ++i)
+            if ((int)rq[run.first + i] - sp.q0 != run.q_hi_rel - i) return -108;
+          expect += run.len;
+        }
+        if (expect != sp.rot_end) return -109;
+      }
+    }
     for (int g : ps.rot_index) {
       if (seen[g]) return -104;
       seen[g] = 1;
@@ -114,5 +131,26 @@ extern "C" int ffb_hostcheck_apply_side(int norb, int nocc, const ffb_givens_rot
   }
   if (n_passes_out) *n_passes_out = (int)sched.passes.size();
   if (n_subs_out) *n_subs_out = total_subs;
+  return 0;
+}
+
+// Print the two-level schedule of a pair-position sequence (developer aid).
+extern "C" int ffb_hostcheck_dump_schedule(int norb, int nocc, const int *q, int n, int64_t smem_bytes,
+                                           int min_cols, int sub_window) {
+  PlanOptions opt = current_options();
+  if (smem_bytes > 0) opt.smem_bytes = smem_bytes;
+  if (min_cols > 0) opt.min_cols = min_cols;
+  if (sub_window > 0) opt.sub_window = sub_window;
+  std::vector<int> qq(q, q + n);
+  SideSchedule sched = build_schedule(norb, nocc, qq, opt);
+  for (size_t ip = 0; ip < sched.passes.size(); ++ip) {
+    const PassSchedule &ps = sched.passes[ip];
+    std::printf("pass %zu: lo=%d W=%d rots=%zu subs=%zu\n", ip, ps.lo, ps.W, ps.rot_index.size(), ps.subs.size());
+    for (const SubPass &sp : ps.subs) {
+      std::printf("  sub q0=%2d w=%d n=%2d :", sp.q0, sp.w, sp.rot_end - sp.rot_begin);
+      for (int r = sp.rot_begin; r < sp.rot_end; ++r) std::printf(" %d", qq[ps.rot_index[r]] - ps.lo - sp.q0);
+      std::printf("\n");
+    }
+  }
   return 0;
 }
