@@ -784,6 +784,16 @@ int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const do
                  (cudaStream_t)stream);
 }
 
+#ifdef FFB_DEBUG_TIMING
+namespace ffb {
+void read_phase_cycles(unsigned long long *out, int reset);
+}
+int ffb_debug_phase_cycles(unsigned long long *out, int reset) {
+  ffb::read_phase_cycles(out, reset);
+  return FFB_OK;
+}
+#endif
+
 #ifdef FFB_DEBUG_KNOBS
 int ffb_debug_knobs(int v) {
   ffb::set_debug_knobs(v);

@@ -83,13 +83,13 @@ struct DiagParams {
 
 constexpr int kChunkBits = 6;                  // beta-string bits per lookup table
 constexpr int kChunkSize = 1 << kChunkBits;    // entries per table
-constexpr int kRowsPerWarp = 2;                // alpha rows a warp streams together
-constexpr int kDiagUnroll = 2;
+// A warp streams RPW alpha rows together, UNR column groups in flight: (2, 2) amortises the beta
+// string / factor loads for big states, (1, 4) gives twice the warps when there are few rows.
 
 // One warp owns kRowsPerWarp alpha rows at a time: it builds their lookup tables in its
 // private slice of shared memory, then streams the rows together so that the beta string
 // and the beta factor of a column are loaded once for all of them.
-template <class S, bool CONTRACT>
+template <class S, bool CONTRACT, int kRowsPerWarp, int kDiagUnroll>
 __global__ void __launch_bounds__(128, 6) diag_kernel(const DiagParams p) {
   using T = typename S::T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -320,32 +320,23 @@ cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t
   const int threads = 128, wpb = threads / 32;
   const int nch = (norb + kChunkBits - 1) / kChunkBits;
   const size_t elem = contract ? sizeof(double) : sizeof(double2);
-  const size_t smem = mab ? (size_t)wpb * kRowsPerWarp * (32 + nch * kChunkSize) * elem : 0;
-  const long long n_groups = (n_rows + kRowsPerWarp - 1) / kRowsPerWarp;
+  // few rows (state of a few hundred MB): one row per warp so that the grid fills the SMs
+  const int rpw = n_rows >= (long long)sm_count * 24 * 2 ? 2 : 1;
+  const size_t smem = mab ? (size_t)wpb * rpw * (32 + nch * kChunkSize) * elem : 0;
+  const long long n_groups = (n_rows + rpw - 1) / rpw;
   long long blocks = (n_groups + wpb - 1) / wpb;
   const long long cap = (long long)sm_count * 16;
   if (blocks > cap) blocks = cap;
-  cudaError_t e = cudaSuccess;
-  if (contract) {
-    static size_t conf = 48 * 1024;
-    if (smem > conf) {
-      e = cudaFuncSetAttribute(diag_kernel<Re, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem);
+  auto launch = [&](auto kernel) -> cudaError_t {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      conf = smem;
     }
-    diag_kernel<Re, true><<<(int)blocks, threads, smem, stream>>>(p);
-  } else {
-    static size_t conf = 48 * 1024;
-    if (smem > conf) {
-      e = cudaFuncSetAttribute(diag_kernel<Cx, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem);
-      if (e != cudaSuccess) return e;
-      conf = smem;
-    }
-    diag_kernel<Cx, false><<<(int)blocks, threads, smem, stream>>>(p);
-  }
-  return cudaGetLastError();
+    kernel<<<(int)blocks, threads, smem, stream>>>(p);
+    return cudaGetLastError();
+  };
+  if (contract) return rpw == 2 ? launch(diag_kernel<Re, true, 2, 2>) : launch(diag_kernel<Re, true, 1, 4>);
+  return rpw == 2 ? launch(diag_kernel<Cx, false, 2, 2>) : launch(diag_kernel<Cx, false, 1, 4>);
 }
 
 cudaError_t launch_vdot(const void *x, const void *y, long long n, void *partial, int n_partial,

@@ -27,6 +27,21 @@ __device__ int g_debug_knobs = 0;
 #define FFB_KNOB(bit) 0
 #endif
 
+#ifdef FFB_DEBUG_TIMING
+// per-phase cycle counters (developer builds only): lane 0 of every warp accumulates clock64() deltas
+__device__ unsigned long long g_phase_cycles[16];
+#define FFB_T0() long long _t0 = clock64()
+#define FFB_TACC(k)                                                              \
+  do {                                                                           \
+    long long _t1 = clock64();                                                   \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(_t1 - _t0)); \
+    _t0 = _t1;                                                                   \
+  } while (0)
+#else
+#define FFB_T0()
+#define FFB_TACC(k)
+#endif
+
 // ---------------------------------------------------------------- constexpr combinatorics
 __host__ __device__ constexpr int cbinom(int n, int k) {
   if (k < 0 || k > n) return 0;
@@ -129,6 +144,7 @@ __device__ __forceinline__ void process_item(double2 *__restrict__ tile, int col
   const uint16_t *o = offtab + (entry >> 24) * kOffRow + cclass_offset(W, M);
   double2 a[N];
   unsigned idx2[(N + 1) / 2];  // tile indices, two 16-bit values per register
+  FFB_T0();
 #pragma unroll
   for (int t = 0; t < N; ++t) {
     const unsigned i = (unsigned)((base + (int)o[t]) * cols + col);
@@ -138,6 +154,7 @@ __device__ __forceinline__ void process_item(double2 *__restrict__ tile, int col
     else
       idx2[t >> 1] = i;
   }
+  FFB_TACC(3);
   // one dispatch per run; the next run's descriptor is fetched while the current one executes
   int code = p.runcode[run0], r = p.runrot[run0];
   for (int run = run0; run < (FFB_KNOB(4) ? run0 : run1); ++run) {
@@ -146,8 +163,10 @@ __device__ __forceinline__ void process_item(double2 *__restrict__ tile, int col
     code = code_n;
     r = r_n;
   }
+  FFB_TACC(4);
 #pragma unroll
   for (int t = 0; t < N; ++t) tile[(t & 1) ? (idx2[t >> 1] >> 16) : (idx2[t >> 1] & 0xFFFFu)] = a[t];
+  FFB_TACC(5);
 }
 
 template <int W, int M = 1>
@@ -258,6 +277,7 @@ __global__ void __launch_bounds__(512, 1)
     const int n_el = R * cols;
     const bool row_major = p.col_stride == 1;  // batch index contiguous in memory
 
+    FFB_T0();
     // ---- load the tile: kLoadUnroll independent (table -> global -> shared) chains per thread
     for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
       double2 v[kLoadUnroll];
@@ -285,6 +305,7 @@ __global__ void __launch_bounds__(512, 1)
       for (int u = 0; u < kLoadUnroll; ++u)
         if (dst[u] >= 0) tile[dst[u]] = v[u];
     }
+    FFB_TACC(0);
     const bool work = G.has_blocks && p.n_sub > 0;
     if (work) {
       for (int e = tid; e < kOffTabEntries / 8; e += nthr)
@@ -298,6 +319,7 @@ __global__ void __launch_bounds__(512, 1)
       cp_async_wait_all();
     }
     __syncthreads();
+    FFB_TACC(1);
     cached_group = work ? gi : cached_group;
 
     // ---- sub-passes
@@ -335,14 +357,20 @@ __global__ void __launch_bounds__(512, 1)
             nxt.mp = 0;
             nxt.col = 0;
           }
+          FFB_TACC(2);
           if (have && cur.mp && !FFB_KNOB(8))
             process_dispatch<W>(cur.mp, tile, cols, cur.col, cur.entry, offtab, p, run0, run1);
+#ifdef FFB_DEBUG_TIMING
+          _t0 = clock64();
+#endif
           cur = nxt;
           if (g_next >= n_chunks) break;
           g = g_next;
         }
         cp_async_wait_all();
+        FFB_TACC(2);
         if (!FFB_KNOB(1)) __syncthreads();
+        FFB_TACC(6);
       }
     }
 
@@ -372,7 +400,9 @@ __global__ void __launch_bounds__(512, 1)
         }
       }
     }
+    FFB_TACC(7);
     __syncthreads();
+    FFB_TACC(6);
   }
 }
 
@@ -419,6 +449,16 @@ int fused_pass_ctas_per_sm(int w, int threads, size_t tile_bytes) {
 
 #ifdef FFB_DEBUG_KNOBS
 void set_debug_knobs(int v) { cudaMemcpyToSymbol(g_debug_knobs, &v, sizeof(int)); }
+#endif
+#ifdef FFB_DEBUG_TIMING
+void read_phase_cycles(unsigned long long *out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  }
+}
 #endif
 
 cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t tile_bytes,
