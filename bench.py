@@ -224,6 +224,18 @@ def run_ours(args):
         diag_gbs = diag["bytes"] / (diag["ms"] * 1e-3) / 1e9 if diag["ms"] > 0 else 0.0
         plan = get_plan(NORB, NELEC, u, u)
         n_launch = sum(v["launches"] for v in prof.values())
+        # second ceiling of the fused kernel: the FP64 pipe.  One rotation on one amplitude pair is
+        # 4 DMUL + 8 DFMA; a rotation of one spin touches C(norb-2, nocc-1) * dim_other pairs.
+        import math
+
+        from ffsim_b200.linalg import givens_decomposition
+        n_rot = len(givens_decomposition(u)[0])
+        pairs = math.comb(NORB - 2, NELEC[0] - 1) * math.comb(NORB, NELEC[1])
+        dfma_per_launch = 12.0 * n_rot * pairs
+        fp64_peak = float(peaks.get("fp64_tflops", 36.8))  # scripts/micro/fp64_peak.cu on this pool: profiles/r1_fp64_peak.jsonl
+        fp64_tflops = 2.0 * dfma_per_launch / (fused["ms"] / launches_timed * 1e-3) / 1e12 if fused["ms"] > 0 else 0.0
+        hbm_floor_ms = fused["bytes"] / launches_timed / (peak * 1e9) * 1e3
+        fp64_floor_ms = 2.0 * dfma_per_launch / (fp64_peak * 1e12) * 1e3
         cpu_value, cpu_sec, cores = time_cpu(3, 1)
         line = {
             "metric": METRIC,
@@ -253,9 +265,17 @@ def run_ours(args):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "launches": fused["launches"], "avg_launch_ms": fused["ms"] / launches_timed,
                          "algorithmic_bytes_per_launch": fused["bytes"] / launches_timed,
-                         "note": "32 B per amplitude touched per launch; each launch fuses all "
-                                 "n(n-1)/2 Givens rotations + phases of one spin sector, so it is FP64-pipe "
-                                 "bound rather than HBM bound (see DESIGN.md)",
+                         "note": "32 B per amplitude per launch; each launch fuses all n(n-1)/2 Givens rotations "
+                                 "+ phases of one spin sector into one HBM round trip, which makes the FP64 pipe "
+                                 "(not HBM) the binding ceiling: see fp64 below and DESIGN.md 4.1",
+                         "fp64": {"rotations_per_launch": n_rot, "dfma_pipe_ops_per_launch": dfma_per_launch,
+                                  "achieved_tflops": fp64_tflops, "peak_tflops": fp64_peak,
+                                  "peak_source": "measured DFMA throughput, scripts/micro/fp64_peak.cu "
+                                                 "(profiles/r1_fp64_peak.jsonl)",
+                                  "frac": fp64_tflops / fp64_peak, "floor_ms": fp64_floor_ms},
+                         "hbm_floor_ms": hbm_floor_ms,
+                         "frac_of_binding_roofline": max(hbm_floor_ms, fp64_floor_ms) / (fused["ms"] / launches_timed)
+                         if fused["ms"] > 0 else 0.0,
                          "diag_kernel": {"achieved": diag_gbs, "frac": diag_gbs / peak,
                                          "avg_launch_ms": diag["ms"] / max(diag["timed"], 1)},
                          "step_algorithmic_TBps": 96.0 * dim / (elapsed_ms / args.steps * 1e-3) / 1e12},

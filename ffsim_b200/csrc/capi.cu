@@ -19,6 +19,11 @@ namespace ffb {
 void set_debug_knobs(int v);
 }
 #endif
+#ifdef FFB_DEBUG_TIMING
+namespace ffb {
+void read_phase_cycles(unsigned long long *out, int reset);
+}
+#endif
 
 static_assert(ffb::kMaxLow == ffb::kMaxLowDev, "kMaxLow mismatch");
 
@@ -785,9 +790,6 @@ int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const do
 }
 
 #ifdef FFB_DEBUG_TIMING
-namespace ffb {
-void read_phase_cycles(unsigned long long *out, int reset);
-}
 int ffb_debug_phase_cycles(unsigned long long *out, int reset) {
   ffb::read_phase_cycles(out, reset);
   return FFB_OK;

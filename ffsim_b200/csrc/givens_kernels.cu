@@ -28,14 +28,16 @@ __device__ int g_debug_knobs = 0;
 #endif
 
 #ifdef FFB_DEBUG_TIMING
-// per-phase cycle counters (developer builds only): lane 0 of every warp accumulates clock64() deltas
+// per-phase cycle counters (developer builds only): lane 0 of every warp accumulates clock64()
+// deltas in a private shared-memory row; rows are flushed to global memory when the CTA ends
 __device__ unsigned long long g_phase_cycles[16];
+__shared__ unsigned long long s_phase_cycles[32][8];
 #define FFB_T0() long long _t0 = clock64()
-#define FFB_TACC(k)                                                              \
-  do {                                                                           \
-    long long _t1 = clock64();                                                   \
-    if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(_t1 - _t0)); \
-    _t0 = _t1;                                                                   \
+#define FFB_TACC(k)                                                                  \
+  do {                                                                               \
+    long long _t1 = clock64();                                                       \
+    if ((threadIdx.x & 31) == 0) s_phase_cycles[threadIdx.x >> 5][k] += (unsigned long long)(_t1 - _t0); \
+    _t0 = clock64();                                                                 \
   } while (0)
 #else
 #define FFB_T0()
@@ -182,9 +184,12 @@ __device__ __forceinline__ void process_dispatch(int mp, double2 *tile, int cols
 }
 
 constexpr int kOffTabEntries = kMaxLowDev * kOffRow;  // u16 entries of one sub-pass table
-// shared-memory prefix: two block-offset tables + the group's per-sub-pass block lists
+constexpr int kChunkRow = 8;  // u16 per sub-pass: chunk-prefix of <= kMaxSeg segments, pad, total
+static_assert(kMaxSeg + 1 < kChunkRow, "chunk row too short");
+// shared-memory prefix: two block-offset tables + the group's per-sub-pass block lists + chunk prefixes
+constexpr size_t kGsubBytes = (kMaxSubPerPass * sizeof(GroupSubDev) + 15) / 16 * 16;
 constexpr size_t kFusedSmemOverhead =
-    ((2 * kOffTabEntries * sizeof(uint16_t) + kMaxSubPerPass * sizeof(GroupSubDev)) + 15) / 16 * 16;
+    2 * kOffTabEntries * sizeof(uint16_t) + kGsubBytes + kMaxSubPerPass * kChunkRow * sizeof(uint16_t);
 
 // 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, no stall at issue
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -205,42 +210,35 @@ struct ChunkWork {
   int col;
 };
 
-// The g-th chunk of the concatenated (heavy classes first) chunk list of a sub-pass.
-__device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const uint32_t *__restrict__ u32,
-                                                 int g, int lane, int cols, unsigned inv_cols) {
+// The g-th chunk of the concatenated (heavy classes first) chunk list of a sub-pass.  `cend` is the
+// sub-pass's row of the chunk-prefix table: cend[k] = chunks in segments 0..k (0xFFFF past the last
+// segment), cend[kChunkRow-1] = total.  One 16-byte shared load finds the segment.
+__device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const uint16_t *cend,
+                                                 const uint32_t *__restrict__ u32, int g, int lane,
+                                                 int cols, unsigned inv_cols) {
   ChunkWork w;
   w.entry = 0;
   w.mp = 0;
   w.col = 0;
-  int base = 0;
-  for (int sg = 0; sg < gs.n_seg; ++sg) {
-    const int n_items = gs.seg[sg].count * cols;
-    const int n_chunks = (n_items + 31) >> 5;
-    if (g < base + n_chunks) {
-      const int item = ((g - base) << 5) + lane;
-      if (item < n_items) {
-        const int blk = fast_div(item, inv_cols);
-        w.col = item - blk * cols;
-        w.mp = gs.seg[sg].mp;
-        w.entry = u32[gs.blocks_off + gs.seg[sg].begin + blk];
-      }
-      return w;
-    }
-    base += n_chunks;
+  const uint4 pk = *reinterpret_cast<const uint4 *>(cend);
+  const int c0 = pk.x & 0xFFFF, c1 = pk.x >> 16, c2 = pk.y & 0xFFFF, c3 = pk.y >> 16, c4 = pk.z & 0xFFFF;
+  static_assert(kMaxSeg == 5, "fetch_chunk unpacks five segment prefixes");
+  if (g >= (int)(pk.w >> 16)) return w;
+  int sg = 0, base = 0;
+  if (g >= c0) sg = 1, base = c0;
+  if (g >= c1) sg = 2, base = c1;
+  if (g >= c2) sg = 3, base = c2;
+  if (g >= c3) sg = 4, base = c3;
+  (void)c4;
+  const SegDev seg = gs.seg[sg];
+  const int item = ((g - base) << 5) + lane;
+  if (item < seg.count * cols) {
+    const int blk = fast_div(item, inv_cols);
+    w.col = item - blk * cols;
+    w.mp = seg.mp;
+    w.entry = u32[gs.blocks_off + seg.begin + blk];
   }
   return w;
-}
-
-__device__ __forceinline__ int total_chunks(const GroupSubDev &gs, int cols) {
-  int n = 0;
-  for (int sg = 0; sg < gs.n_seg; ++sg) n += (gs.seg[sg].count * cols + 31) >> 5;
-  return n;
-}
-
-// k-th chunk position of warp `warp` when chunks are dealt to warps in snake order
-// (0..nw-1, nw-1..0, ...): with the list sorted by decreasing cost this balances the warps.
-__device__ __forceinline__ int snake_pos(int k, int warp, int nwarp) {
-  return k * nwarp + ((k & 1) ? (nwarp - 1 - warp) : warp);
 }
 
 constexpr int kLoadUnroll = 8;
@@ -251,11 +249,16 @@ __global__ void __launch_bounds__(512, 1)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint16_t *offbuf = reinterpret_cast<uint16_t *>(smem_raw);  // 2 x kOffTabEntries
   GroupSubDev *gsub_s = reinterpret_cast<GroupSubDev *>(smem_raw + 2 * kOffTabEntries * sizeof(uint16_t));
+  uint16_t *cend_s = reinterpret_cast<uint16_t *>(smem_raw + 2 * kOffTabEntries * sizeof(uint16_t) + kGsubBytes);
   double2 *tile = reinterpret_cast<double2 *>(smem_raw + kFusedSmemOverhead);
   __shared__ int chunk_ctr[2];
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+#ifdef FFB_DEBUG_TIMING
+  if (tid < 32 * 8) s_phase_cycles[tid >> 3][tid & 7] = 0;
+  __syncthreads();
+#endif
   double2 *__restrict__ data = reinterpret_cast<double2 *>(p.data);
   const double2 *__restrict__ rowphase = reinterpret_cast<const double2 *>(p.rowphase);
   int cached_group = -1;
@@ -278,28 +281,34 @@ __global__ void __launch_bounds__(512, 1)
     const bool row_major = p.col_stride == 1;  // batch index contiguous in memory
 
     FFB_T0();
-    // ---- load the tile: kLoadUnroll independent (table -> global -> shared) chains per thread
+    // ---- load the tile.  Each element needs its row offset from the (global) tile row table first:
+    // all kLoadUnroll table loads are issued before the first data load, so that a batch costs two
+    // memory latencies instead of 2 * kLoadUnroll (the issue order is the program order).
     for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
-      double2 v[kLoadUnroll];
-      int dst[kLoadUnroll];
+      int dst[kLoadUnroll], jj[kLoadUnroll];
+      uint32_t trow[kLoadUnroll];
 #pragma unroll
       for (int u = 0; u < kLoadUnroll; ++u) {
         const int e = e0 + u * nthr;
-        v[u] = make_double2(0.0, 0.0);
-        dst[u] = -1;
-        if (e < n_el) {
-          int r, j;
-          if (row_major) {
-            r = fast_div(e, inv_cols);
-            j = e - r * cols;
-          } else {
-            j = fast_div(e, inv_R);
-            r = e - j * R;
-          }
-          dst[u] = r * cols + j;
-          if (j < ncv && !FFB_KNOB(2))
-            v[u] = data[(long long)(rowbase + tab[r]) * p.row_stride + (col0 + j) * p.col_stride];
+        const int ec = e < n_el ? e : 0;
+        int r, j;
+        if (row_major) {
+          r = fast_div(ec, inv_cols);
+          j = ec - r * cols;
+        } else {
+          j = fast_div(ec, inv_R);
+          r = ec - j * R;
         }
+        dst[u] = e < n_el ? r * cols + j : -1;
+        jj[u] = j;
+        trow[u] = tab[r];
+      }
+      double2 v[kLoadUnroll];
+#pragma unroll
+      for (int u = 0; u < kLoadUnroll; ++u) {
+        v[u] = make_double2(0.0, 0.0);
+        if (dst[u] >= 0 && jj[u] < ncv && !FFB_KNOB(2))
+          v[u] = data[(long long)(rowbase + trow[u]) * p.row_stride + (col0 + jj[u]) * p.col_stride];
       }
 #pragma unroll
       for (int u = 0; u < kLoadUnroll; ++u)
@@ -314,6 +323,19 @@ __global__ void __launch_bounds__(512, 1)
         const uint32_t *src = reinterpret_cast<const uint32_t *>(p.gsub + G.gsub_off);
         const int n32 = p.n_sub * (int)(sizeof(GroupSubDev) / 4);
         for (int e = tid; e < n32; e += nthr) reinterpret_cast<uint32_t *>(gsub_s)[e] = src[e];
+        // chunk-prefix rows for this group's column count (read straight from global: the copy
+        // above is not visible yet)
+        for (int sp = tid; sp < p.n_sub; sp += nthr) {
+          const GroupSubDev &gsrc = p.gsub[G.gsub_off + sp];
+          uint16_t *row = cend_s + sp * kChunkRow;
+          int acc = 0;
+#pragma unroll
+          for (int k = 0; k < kChunkRow - 1; ++k) {
+            if (k < gsrc.n_seg && k < kMaxSeg) acc += (gsrc.seg[k].count * cols + 31) >> 5;
+            row[k] = (k < gsrc.n_seg && k < kMaxSeg) ? (uint16_t)acc : (uint16_t)0xFFFF;
+          }
+          row[kChunkRow - 1] = (uint16_t)acc;
+        }
       }
       if (tid == 0) chunk_ctr[0] = nwarp;
       cp_async_wait_all();
@@ -324,7 +346,10 @@ __global__ void __launch_bounds__(512, 1)
 
     // ---- sub-passes
     if (work) {
-      ChunkWork cur = fetch_chunk(gsub_s[0], p.u32, warp, lane, cols, inv_cols);
+      // chunks 0..nwarp-1 of a sub-pass are owned statically (their descriptors are fetched before
+      // the previous barrier); the rest are handed out through a shared counter, heaviest class
+      // first, which keeps the warps balanced at the barrier
+      ChunkWork cur = fetch_chunk(gsub_s[0], cend_s, p.u32, warp, lane, cols, inv_cols);
       for (int s = 0; s < p.n_sub; ++s) {
         const uint16_t *offtab = offbuf + (s & 1) * kOffTabEntries;
         if (s + 1 < p.n_sub) {  // prefetch the next sub-pass's offset table (lands before the barrier)
@@ -333,32 +358,31 @@ __global__ void __launch_bounds__(512, 1)
           for (int e = tid; e < kOffTabEntries / 8; e += nthr) cp_async16(dst + 8 * e, src + 8 * e);
         }
         const GroupSubDev &gs = gsub_s[s];
+        const uint16_t *cend = cend_s + s * kChunkRow;
         const int run0 = p.sub[s].run_begin, run1 = p.sub[s].run_end;
-        const int n_chunks = total_chunks(gs, cols);
-        // chunks 0..nwarp-1 are owned statically (their descriptors were prefetched before the
-        // previous barrier); the rest are handed out dynamically, heaviest first
+        const int n_chunks = cend[kChunkRow - 1];
         int *ctr = &chunk_ctr[s & 1];
         if (tid == 0) chunk_ctr[(s + 1) & 1] = nwarp;
         int g = warp;
         while (true) {
-          const bool have = g < n_chunks;
+          const bool mine = g < n_chunks;
           int g_next = n_chunks;
-          if (have) {
+          if (mine) {
             if (lane == 0) g_next = atomicAdd(ctr, 1);
             g_next = __shfl_sync(0xffffffffu, g_next, 0);
           }
           ChunkWork nxt;
           if (g_next < n_chunks) {
-            nxt = fetch_chunk(gs, p.u32, g_next, lane, cols, inv_cols);
+            nxt = fetch_chunk(gs, cend, p.u32, g_next, lane, cols, inv_cols);
           } else if (s + 1 < p.n_sub) {
-            nxt = fetch_chunk(gsub_s[s + 1], p.u32, warp, lane, cols, inv_cols);
+            nxt = fetch_chunk(gsub_s[s + 1], cend + kChunkRow, p.u32, warp, lane, cols, inv_cols);
           } else {
             nxt.entry = 0;
             nxt.mp = 0;
             nxt.col = 0;
           }
           FFB_TACC(2);
-          if (have && cur.mp && !FFB_KNOB(8))
+          if (mine && cur.mp && !FFB_KNOB(8))
             process_dispatch<W>(cur.mp, tile, cols, cur.col, cur.entry, offtab, p, run0, run1);
 #ifdef FFB_DEBUG_TIMING
           _t0 = clock64();
@@ -374,29 +398,38 @@ __global__ void __launch_bounds__(512, 1)
       }
     }
 
-    // ---- store the tile (and fold the per-row phase product in on the last pass)
+    // ---- store the tile (and fold the per-row phase product in on the last pass); table and phase
+    // loads are batched ahead of the stores like in the load loop
     for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
+      int src[kLoadUnroll], jj[kLoadUnroll];
+      uint32_t grow[kLoadUnroll];
 #pragma unroll
       for (int u = 0; u < kLoadUnroll; ++u) {
         const int e = e0 + u * nthr;
-        if (e < n_el) {
-          int r, j;
-          if (row_major) {
-            r = fast_div(e, inv_cols);
-            j = e - r * cols;
-          } else {
-            j = fast_div(e, inv_R);
-            r = e - j * R;
-          }
-          if (j < ncv && !FFB_KNOB(2)) {
-            double2 v = tile[r * cols + j];
-            const uint32_t row = rowbase + tab[r];
-            if (rowphase) {
-              const double2 f = rowphase[row];
-              v = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
-            }
-            data[(long long)row * p.row_stride + (col0 + j) * p.col_stride] = v;
-          }
+        const int ec = e < n_el ? e : 0;
+        int r, j;
+        if (row_major) {
+          r = fast_div(ec, inv_cols);
+          j = ec - r * cols;
+        } else {
+          j = fast_div(ec, inv_R);
+          r = ec - j * R;
+        }
+        src[u] = (e < n_el && j < ncv && !FFB_KNOB(2)) ? r * cols + j : -1;
+        jj[u] = j;
+        grow[u] = rowbase + tab[r];
+      }
+      double2 f[kLoadUnroll];
+      if (rowphase) {
+#pragma unroll
+        for (int u = 0; u < kLoadUnroll; ++u) f[u] = rowphase[grow[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < kLoadUnroll; ++u) {
+        if (src[u] >= 0) {
+          double2 v = tile[src[u]];
+          if (rowphase) v = make_double2(v.x * f[u].x - v.y * f[u].y, v.x * f[u].y + v.y * f[u].x);
+          data[(long long)grow[u] * p.row_stride + (col0 + jj[u]) * p.col_stride] = v;
         }
       }
     }
@@ -404,6 +437,10 @@ __global__ void __launch_bounds__(512, 1)
     __syncthreads();
     FFB_TACC(6);
   }
+#ifdef FFB_DEBUG_TIMING
+  __syncthreads();
+  if (tid < nwarp * 8) atomicAdd(&g_phase_cycles[tid & 7], s_phase_cycles[tid >> 3][tid & 7]);
+#endif
 }
 
 template <int W>
