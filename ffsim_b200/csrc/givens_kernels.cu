@@ -103,16 +103,20 @@ __device__ __forceinline__ void rot_block(double2 (&a)[cbinom(W, M)], double c, 
 template <int W, int M, int QHI, int LEN>
 __device__ __forceinline__ void run_block(double2 (&a)[cbinom(W, M)], const PassParams &p, int r) {
   if constexpr (QHI <= W - 2 && QHI - LEN + 1 >= 0) {
-    double c[LEN], sr[LEN], si[LEN];
-#pragma unroll
-    for (int i = 0; i < LEN; ++i) {
-      c[i] = p.rc[r + i];
-      sr[i] = p.rsr[r + i];
-      si[i] = p.rsi[r + i];
+    // coefficients are fetched rotation by rotation (6 registers live, not 6 * LEN): the widest
+    // register block leaves no room for more
+    {
+      const double c = p.rc[r], sr = p.rsr[r], si = p.rsi[r];
+      rot_block<W, M, QHI>(a, c, sr, si);
     }
-    if constexpr (LEN >= 1) rot_block<W, M, QHI>(a, c[0], sr[0], si[0]);
-    if constexpr (LEN >= 2) rot_block<W, M, QHI - 1>(a, c[1], sr[1], si[1]);
-    if constexpr (LEN >= 3) rot_block<W, M, QHI - 2>(a, c[2], sr[2], si[2]);
+    if constexpr (LEN >= 2) {
+      const double c = p.rc[r + 1], sr = p.rsr[r + 1], si = p.rsi[r + 1];
+      rot_block<W, M, QHI - 1>(a, c, sr, si);
+    }
+    if constexpr (LEN >= 3) {
+      const double c = p.rc[r + 2], sr = p.rsr[r + 2], si = p.rsi[r + 2];
+      rot_block<W, M, QHI - 2>(a, c, sr, si);
+    }
   }
 }
 
@@ -259,60 +263,64 @@ __global__ void __launch_bounds__(512, 1)
   if (tid < 32 * 8) s_phase_cycles[tid >> 3][tid & 7] = 0;
   __syncthreads();
 #endif
-  double2 *__restrict__ data = reinterpret_cast<double2 *>(p.data);
-  const double2 *__restrict__ rowphase = reinterpret_cast<const double2 *>(p.rowphase);
   int cached_group = -1;
 
   for (long long unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
     int gi = 0;
     while (gi + 1 < p.n_groups && unit >= p.g[gi + 1].unit_begin) ++gi;
     const GroupLaunch &G = p.g[gi];
-    const long long local = unit - G.unit_begin;
-    const long long combo = local / G.n_strips;
-    const long long strip = local - combo * G.n_strips;
-    const int R = G.R, cols = G.cols;
-    const unsigned inv_cols = G.inv_cols, inv_R = G.inv_R;
-    const long long col0 = strip * cols;
-    const int ncv = (int)min((long long)cols, p.n_cols - col0);
-    const uint32_t rowbase = p.u32[G.combo_base_off + combo];
-    const uint32_t *__restrict__ tab =
-        p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
-    const int n_el = R * cols;
-    const bool row_major = p.col_stride == 1;  // batch index contiguous in memory
+    const int cols = G.cols;
+    const unsigned inv_cols = G.inv_cols;
 
     FFB_T0();
-    // ---- load the tile.  Each element needs its row offset from the (global) tile row table first:
-    // all kLoadUnroll table loads are issued before the first data load, so that a batch costs two
-    // memory latencies instead of 2 * kLoadUnroll (the issue order is the program order).
-    for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
-      int dst[kLoadUnroll], jj[kLoadUnroll];
-      uint32_t trow[kLoadUnroll];
+    {
+      // ---- load the tile.  (The tile geometry is decoded here and again before the store, in a
+      // scope of its own, so that none of it stays in registers across the sub-passes.)
+      double2 *__restrict__ data = reinterpret_cast<double2 *>(p.data);
+      const long long local = unit - G.unit_begin;
+      const long long combo = local / G.n_strips;
+      const long long strip = local - combo * G.n_strips;
+      const int R = G.R;
+      const unsigned inv_R = G.inv_R;
+      const long long col0 = strip * cols;
+      const int ncv = (int)min((long long)cols, p.n_cols - col0);
+      const uint32_t rowbase = p.u32[G.combo_base_off + combo];
+      const uint32_t *__restrict__ tab = p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
+      const int n_el = R * cols;
+      const bool row_major = p.col_stride == 1;  // batch index contiguous in memory
+      // Each element needs its row offset from the (global) tile row table first: all kLoadUnroll
+      // table loads are issued before the first data load, so that a batch costs two memory
+      // latencies instead of 2 * kLoadUnroll (the issue order is the program order).
+      for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
+        int dst[kLoadUnroll], jj[kLoadUnroll];
+        uint32_t trow[kLoadUnroll];
 #pragma unroll
-      for (int u = 0; u < kLoadUnroll; ++u) {
-        const int e = e0 + u * nthr;
-        const int ec = e < n_el ? e : 0;
-        int r, j;
-        if (row_major) {
-          r = fast_div(ec, inv_cols);
-          j = ec - r * cols;
-        } else {
-          j = fast_div(ec, inv_R);
-          r = ec - j * R;
+        for (int u = 0; u < kLoadUnroll; ++u) {
+          const int e = e0 + u * nthr;
+          const int ec = e < n_el ? e : 0;
+          int r, j;
+          if (row_major) {
+            r = fast_div(ec, inv_cols);
+            j = ec - r * cols;
+          } else {
+            j = fast_div(ec, inv_R);
+            r = ec - j * R;
+          }
+          dst[u] = e < n_el ? r * cols + j : -1;
+          jj[u] = j;
+          trow[u] = tab[r];
         }
-        dst[u] = e < n_el ? r * cols + j : -1;
-        jj[u] = j;
-        trow[u] = tab[r];
-      }
-      double2 v[kLoadUnroll];
+        double2 v[kLoadUnroll];
 #pragma unroll
-      for (int u = 0; u < kLoadUnroll; ++u) {
-        v[u] = make_double2(0.0, 0.0);
-        if (dst[u] >= 0 && jj[u] < ncv && !FFB_KNOB(2))
-          v[u] = data[(long long)(rowbase + trow[u]) * p.row_stride + (col0 + jj[u]) * p.col_stride];
-      }
+        for (int u = 0; u < kLoadUnroll; ++u) {
+          v[u] = make_double2(0.0, 0.0);
+          if (dst[u] >= 0 && jj[u] < ncv && !FFB_KNOB(2))
+            v[u] = data[(long long)(rowbase + trow[u]) * p.row_stride + (col0 + jj[u]) * p.col_stride];
+        }
 #pragma unroll
-      for (int u = 0; u < kLoadUnroll; ++u)
-        if (dst[u] >= 0) tile[dst[u]] = v[u];
+        for (int u = 0; u < kLoadUnroll; ++u)
+          if (dst[u] >= 0) tile[dst[u]] = v[u];
+      }
     }
     FFB_TACC(0);
     const bool work = G.has_blocks && p.n_sub > 0;
@@ -400,36 +408,53 @@ __global__ void __launch_bounds__(512, 1)
 
     // ---- store the tile (and fold the per-row phase product in on the last pass); table and phase
     // loads are batched ahead of the stores like in the load loop
-    for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
-      int src[kLoadUnroll], jj[kLoadUnroll];
-      uint32_t grow[kLoadUnroll];
+    {
+      long long unit_again = unit;
+      asm volatile("" : "+l"(unit_again));  // decode afresh: keep the geometry out of the sub-pass registers
+      double2 *__restrict__ data = reinterpret_cast<double2 *>(p.data);
+      const double2 *__restrict__ rowphase = reinterpret_cast<const double2 *>(p.rowphase);
+      const long long local = unit_again - G.unit_begin;
+      const long long combo = local / G.n_strips;
+      const long long strip = local - combo * G.n_strips;
+      const int R = G.R;
+      const unsigned inv_R = G.inv_R;
+      const long long col0 = strip * cols;
+      const int ncv = (int)min((long long)cols, p.n_cols - col0);
+      const uint32_t rowbase = p.u32[G.combo_base_off + combo];
+      const uint32_t *__restrict__ tab = p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
+      const int n_el = R * cols;
+      const bool row_major = p.col_stride == 1;
+      for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
+        int src[kLoadUnroll], jj[kLoadUnroll];
+        uint32_t grow[kLoadUnroll];
 #pragma unroll
-      for (int u = 0; u < kLoadUnroll; ++u) {
-        const int e = e0 + u * nthr;
-        const int ec = e < n_el ? e : 0;
-        int r, j;
-        if (row_major) {
-          r = fast_div(ec, inv_cols);
-          j = ec - r * cols;
-        } else {
-          j = fast_div(ec, inv_R);
-          r = ec - j * R;
+        for (int u = 0; u < kLoadUnroll; ++u) {
+          const int e = e0 + u * nthr;
+          const int ec = e < n_el ? e : 0;
+          int r, j;
+          if (row_major) {
+            r = fast_div(ec, inv_cols);
+            j = ec - r * cols;
+          } else {
+            j = fast_div(ec, inv_R);
+            r = ec - j * R;
+          }
+          src[u] = (e < n_el && j < ncv && !FFB_KNOB(2)) ? r * cols + j : -1;
+          jj[u] = j;
+          grow[u] = rowbase + tab[r];
         }
-        src[u] = (e < n_el && j < ncv && !FFB_KNOB(2)) ? r * cols + j : -1;
-        jj[u] = j;
-        grow[u] = rowbase + tab[r];
-      }
-      double2 f[kLoadUnroll];
-      if (rowphase) {
+        double2 f[kLoadUnroll];
+        if (rowphase) {
 #pragma unroll
-        for (int u = 0; u < kLoadUnroll; ++u) f[u] = rowphase[grow[u]];
-      }
+          for (int u = 0; u < kLoadUnroll; ++u) f[u] = rowphase[grow[u]];
+        }
 #pragma unroll
-      for (int u = 0; u < kLoadUnroll; ++u) {
-        if (src[u] >= 0) {
-          double2 v = tile[src[u]];
-          if (rowphase) v = make_double2(v.x * f[u].x - v.y * f[u].y, v.x * f[u].y + v.y * f[u].x);
-          data[(long long)grow[u] * p.row_stride + (col0 + jj[u]) * p.col_stride] = v;
+        for (int u = 0; u < kLoadUnroll; ++u) {
+          if (src[u] >= 0) {
+            double2 v = tile[src[u]];
+            if (rowphase) v = make_double2(v.x * f[u].x - v.y * f[u].y, v.x * f[u].y + v.y * f[u].x);
+            data[(long long)grow[u] * p.row_stride + (col0 + jj[u]) * p.col_stride] = v;
+          }
         }
       }
     }
