@@ -92,6 +92,7 @@ EXPORTS = {
     "ffb_contract_diag_coulomb": (c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int64, c_int64, _P),
     "ffb_contract_num_op_sum": (c_int, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int64, _P),
     "ffb_transpose": (c_int, _P, _P, c_int64, c_int64, c_int64, c_int64, _P),
+    "ffb_exchange_blocks": (c_int, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P),
     "ffb_vdot": (c_int, _P, _P, c_int64, _P, _P),
     "ffb_axpby": (c_int, C128, _P, C128, _P, c_int64, _P),
     "ffb_profile_begin": (c_int,),

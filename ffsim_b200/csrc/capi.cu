@@ -858,6 +858,37 @@ int ffb_transpose(const void *in_dev, void *out_dev, int64_t n_rows, int64_t n_c
   return FFB_OK;
 }
 
+int ffb_exchange_blocks(const void *src_dev, int64_t src_ld, int n_dst, const int64_t *rows,
+                        const int64_t *width, const int64_t *src_off, void *const *dst_dev,
+                        const int64_t *dst_off, const int64_t *dst_ld, void *stream) {
+  if (n_dst == 0) return FFB_OK;
+  if (n_dst < 0 || n_dst > kMaxExchangeDst || !rows || !width || !src_off || !dst_dev || !dst_off || !dst_ld)
+    return fail(FFB_EINVAL, "ffb_exchange_blocks: bad argument");
+  ExchangeParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.src = src_dev;
+  p.src_ld = src_ld;
+  p.n_dst = n_dst;
+  for (int d = 0; d < n_dst; ++d) {
+    if (rows[d] < 0 || width[d] < 0) return fail(FFB_EINVAL, "ffb_exchange_blocks: negative block size");
+    if (rows[d] > 0 && width[d] > 0 && (!src_dev || !dst_dev[d]))
+      return fail(FFB_EINVAL, "ffb_exchange_blocks: NULL buffer");
+    p.rows[d] = width[d] > 0 ? rows[d] : 0;
+    p.width[d] = width[d];
+    p.src_off[d] = src_off[d];
+    p.dst[d] = dst_dev[d];
+    p.dst_off[d] = dst_off[d];
+    p.dst_ld[d] = dst_ld[d];
+    p.max_rows = std::max<long long>(p.max_rows, p.rows[d]);
+  }
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != FFB_OK) return rc;
+  ProfScope prof(kProfOther, 0.0, (cudaStream_t)stream);
+  FFB_CUDA(launch_exchange(p, di.sm_count, (cudaStream_t)stream));
+  return FFB_OK;
+}
+
 int ffb_vdot(const void *x_dev, const void *y_dev, int64_t n, void *result_dev, void *stream) {
   if (!result_dev || n < 0 || (n > 0 && (!x_dev || !y_dev)))
     return fail(FFB_EINVAL, "ffb_vdot: bad argument");

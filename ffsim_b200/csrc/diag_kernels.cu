@@ -90,7 +90,7 @@ constexpr int kChunkSize = 1 << kChunkBits;    // entries per table
 // private slice of shared memory, then streams the rows together so that the beta string
 // and the beta factor of a column are loaded once for all of them.
 template <class S, bool CONTRACT, int kRowsPerWarp, int kDiagUnroll>
-__global__ void __launch_bounds__(128, 6) diag_kernel(const DiagParams p) {
+__global__ void __launch_bounds__(128, (kRowsPerWarp * kDiagUnroll >= 8) ? 4 : 6) diag_kernel(const DiagParams p) {
   using T = typename S::T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -321,7 +321,7 @@ cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t
   const int nch = (norb + kChunkBits - 1) / kChunkBits;
   const size_t elem = contract ? sizeof(double) : sizeof(double2);
   // few rows (state of a few hundred MB): one row per warp so that the grid fills the SMs
-  const int rpw = n_rows >= (long long)sm_count * 24 * 2 ? 2 : 1;
+  const int rpw = n_rows >= (long long)sm_count * 4 ? 2 : 1;  // (1, 4) measured slower than (2, 2) at 4368 rows
   const size_t smem = mab ? (size_t)wpb * rpw * (32 + nch * kChunkSize) * elem : 0;
   const long long n_groups = (n_rows + rpw - 1) / rpw;
   long long blocks = (n_groups + wpb - 1) / wpb;
@@ -335,8 +335,11 @@ cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t
     kernel<<<(int)blocks, threads, smem, stream>>>(p);
     return cudaGetLastError();
   };
+  // a grid of at most one wave is latency bound: keep twice as many loads in flight per lane
+  const bool one_wave = blocks <= (long long)sm_count * 4;
   if (contract) return rpw == 2 ? launch(diag_kernel<Re, true, 2, 2>) : launch(diag_kernel<Re, true, 1, 4>);
-  return rpw == 2 ? launch(diag_kernel<Cx, false, 2, 2>) : launch(diag_kernel<Cx, false, 1, 4>);
+  if (rpw == 2) return one_wave ? launch(diag_kernel<Cx, false, 2, 4>) : launch(diag_kernel<Cx, false, 2, 2>);
+  return launch(diag_kernel<Cx, false, 1, 4>);
 }
 
 cudaError_t launch_vdot(const void *x, const void *y, long long n, void *partial, int n_partial,

@@ -33,6 +33,20 @@ cudaError_t launch_transpose(const void *in, void *out, long long n_rows, long l
 }  // namespace ffb
 
 namespace ffb {
+// One rank's side of the distributed transpose: block d is rows[d] x width[d] elements, read from
+// src + src_off[d] (row stride src_ld) and written to dst[d] + dst_off[d] (row stride dst_ld[d]).
+constexpr int kMaxExchangeDst = 16;
+struct ExchangeParams {
+  const void *src;
+  long long src_ld;
+  int n_dst;
+  long long max_rows;
+  void *dst[kMaxExchangeDst];
+  long long src_off[kMaxExchangeDst], dst_off[kMaxExchangeDst], dst_ld[kMaxExchangeDst];
+  long long rows[kMaxExchangeDst], width[kMaxExchangeDst];
+};
+cudaError_t launch_exchange(const ExchangeParams &p, int sm_count, cudaStream_t stream);
+
 cudaError_t launch_side_factor(bool contract, const uint32_t *strings, long long dim, int norb,
                                const void *mat, int zrep, void *out, int sm_count,
                                cudaStream_t stream);

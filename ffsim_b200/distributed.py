@@ -15,13 +15,19 @@ A ``ShardedVector`` can be passed wherever the public functions take ``vec``
 ``linear_operator(...) @ vec``, ...).  The reference has no counterpart: it is a
 single-process NumPy code.
 
-The redistribution helpers work on CPU tensors with the ``gloo`` backend as well,
-which is how the host-side logic is tested without GPUs.
+Two implementations of the redistribution exist.  On one NVLink/NVSwitch box the shards live
+in symmetric (peer-mapped) memory and ``ffb_exchange_blocks`` stores every block straight into its
+final place in the destination GPU's buffer: one kernel instead of pack + all-to-all + unpack, no
+send/receive staging buffers.  Everywhere else (``gloo`` on CPU tensors -- which is how the host-side
+logic is tested without GPUs -- or ``FFSIM_B200_EXCHANGE=nccl``) it is ``all_to_all_single``.
 """
 
 from __future__ import annotations
 
+import ctypes
 import math
+import os
+import weakref
 from typing import Sequence
 
 import numpy as np
@@ -122,7 +128,18 @@ class ShardedVector:
 
     def vdot(self, other: "ShardedVector") -> complex:
         """<self|other> (conjugate-linear in self), reduced over the ranks."""
-        acc = torch.view_as_real(torch.vdot(self.local, other.local).reshape(1)).clone()
+        if self.local.is_cuda:
+            # the library's deterministic two-stage reduction (64-bit length: a C5 shard has 2.3e9
+            # amplitudes, more than cuBLAS's 32-bit dot accepts)
+            from ffsim_b200 import _device, _lib
+
+            acc = torch.zeros(1, 2, dtype=torch.float64, device=self.local.device)
+            with torch.cuda.device(self.local.device):
+                _device.sync_device()
+                _lib.check(_lib.lib.ffb_vdot(self.local.data_ptr(), other.local.data_ptr(), self.local.numel(),
+                                             acc.data_ptr(), _device.stream_ptr()))
+        else:  # host tensors: the gloo tests of the redistribution logic
+            acc = torch.view_as_real(torch.vdot(self.local, other.local).reshape(1)).clone()
         if self.world > 1:
             dist.all_reduce(acc, group=self.group)
         return complex(acc[0, 0].item(), acc[0, 1].item())
@@ -211,6 +228,120 @@ def all_to_all_bytes(sv: ShardedVector) -> int:
     return 16 * sv.n_rows * (sv.dim_b - own)
 
 
+# ---------------------------------------------------------------------- peer-memory exchange
+
+class _SymmBuffer:
+    """A symmetric-memory buffer: the same allocation made by every rank, each mapped into all others."""
+
+    def __init__(self, numel: int, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        pg = group if group is not None else dist.group.WORLD
+        try:  # needed by some torch versions, a deprecated no-op in others
+            symm_mem.enable_symm_mem_for_group(pg.group_name)
+        except Exception:
+            pass
+        self.tensor = symm_mem.empty(numel, dtype=torch.complex128, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, pg)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.numel = numel
+
+
+_SYMM_POOL: dict[tuple, list[_SymmBuffer]] = {}
+_SYMM_STATE = {"checked": False, "ok": False}
+
+
+def _symm_get(numel: int, device, group) -> _SymmBuffer:
+    """Pooled: symmetric allocations are collective and slow, and every rank takes and returns them at
+    the same points of the (SPMD) program, so the pools stay identical across ranks."""
+    free = _SYMM_POOL.setdefault((id(group), str(device), numel), [])
+    return free.pop() if free else _SymmBuffer(numel, device, group)
+
+
+def _symm_put(buf: _SymmBuffer, device, group) -> None:
+    _SYMM_POOL.setdefault((id(group), str(device), buf.numel), []).append(buf)
+
+
+def p2p_available(sv: "ShardedVector") -> bool:
+    """Peer-memory exchange needs CUDA shards, more than one rank, at most 16 of them on one box with
+    symmetric memory working; the decision is taken collectively so that all ranks agree."""
+    if sv.world == 1 or sv.world > 16 or not sv.device.type == "cuda":
+        return False
+    if os.environ.get("FFSIM_B200_EXCHANGE", "p2p").lower() == "nccl":
+        return False
+    if not _SYMM_STATE["checked"]:
+        ok = 1
+        try:
+            probe = _SymmBuffer(16, sv.device, sv.group)
+            ok = int(len(probe.ptrs) == sv.world and all(probe.ptrs))
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], device=sv.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=sv.group)
+        _SYMM_STATE["ok"] = bool(flag.item())
+        _SYMM_STATE["checked"] = True
+    return _SYMM_STATE["ok"]
+
+
+def _i64(values):
+    return (ctypes.c_int64 * len(values))(*[int(v) for v in values])
+
+
+def _exchange(src: torch.Tensor, src_ld: int, rows, width, src_off, dst_ptrs, dst_off, dst_ld) -> None:
+    from ffsim_b200 import _device, _lib
+
+    n = len(rows)
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(p)) for p in dst_ptrs])
+    _lib.check(_lib.lib.ffb_exchange_blocks(
+        src.data_ptr(), int(src_ld), n, _i64(rows), _i64(width), _i64(src_off), ptrs, _i64(dst_off), _i64(dst_ld),
+        _device.stream_ptr()))
+
+
+def _make_symmetric(sv: "ShardedVector") -> _SymmBuffer:
+    """Move the row shard into symmetric memory (once per vector; it stays there)."""
+    buf = getattr(sv, "_symm", None)
+    if buf is not None and sv.local is not None and sv.local.data_ptr() == buf.tensor.data_ptr():
+        return buf
+    numel = max(max(sv.a_off[r + 1] - sv.a_off[r] for r in range(sv.world)) * sv.dim_b, 1)
+    buf = _symm_get(numel, sv.device, sv.group)
+    view = buf.tensor[: sv.n_rows * sv.dim_b]
+    view.copy_(sv.local)
+    sv.local = view
+    sv._symm = buf
+    weakref.finalize(sv, _symm_put, buf, sv.device, sv.group)
+    return buf
+
+
+def rotate_alpha_p2p(sv: "ShardedVector", plan, stream) -> None:
+    """Alpha-side rotation through peer memory: scatter the row shard into every rank's column shard,
+    rotate locally, scatter back.  Two kernels move data; nothing is packed, staged or unpacked."""
+    from ffsim_b200 import _lib
+
+    w, r = sv.world, sv.rank
+    rows_of = [sv.a_off[d + 1] - sv.a_off[d] for d in range(w)]
+    cols_of = [sv.b_off[d + 1] - sv.b_off[d] for d in range(w)]
+    nb_local = cols_of[r]
+    row_buf = _make_symmetric(sv)
+    col_numel = max(sv.dim_a * max(cols_of), 1)
+    col_buf = _symm_get(col_numel, sv.device, sv.group)
+    try:
+        # every rank may still be reading its column buffer from an earlier exchange
+        col_buf.handle.barrier(channel=0)
+        # row shard -> column shards: block d = my rows x d's columns, lands at my row offset of d's buffer
+        _exchange(sv.local, sv.dim_b, [sv.n_rows] * w, cols_of, [sv.b_off[d] for d in range(w)],
+                  col_buf.ptrs, [sv.a_off[r] * cols_of[d] for d in range(w)], cols_of)
+        col_buf.handle.barrier(channel=0)
+        if nb_local > 0:
+            _lib.check(_lib.lib.ffb_apply_orbital_rotation_rows(
+                plan.handle, 0, col_buf.tensor.data_ptr(), nb_local, nb_local, stream))
+        # column shard -> row shards: block d = d's rows x my columns, lands at my column offset of d's shard
+        _exchange(col_buf.tensor, nb_local, rows_of, [nb_local] * w, [sv.a_off[d] * nb_local for d in range(w)],
+                  row_buf.ptrs, [sv.b_off[r]] * w, [sv.dim_b] * w)
+        col_buf.handle.barrier(channel=0)
+    finally:
+        _symm_put(col_buf, sv.device, sv.group)
+
+
 # ---------------------------------------------------------------------- device ops on shards
 
 def rotate(sv: ShardedVector, mat_a, mat_b) -> None:
@@ -233,7 +364,9 @@ def rotate(sv: ShardedVector, mat_a, mat_b) -> None:
                     plan.handle, 1, ws.data_ptr(), sv.n_rows, sv.n_rows, stream))
                 _lib.check(_lib.lib.ffb_transpose(ws.data_ptr(), sv.local.data_ptr(), sv.dim_b, sv.n_rows,
                                                   sv.n_rows, sv.dim_b, stream))
-        if mat_a is not None:
+        if mat_a is not None and p2p_available(sv):
+            rotate_alpha_p2p(sv, plan, stream)
+        elif mat_a is not None:
             cols = to_column_shards(sv, release=True)
             nb_local = cols.shape[1]
             if nb_local > 0:

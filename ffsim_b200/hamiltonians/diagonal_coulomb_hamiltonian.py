@@ -57,11 +57,11 @@ class DiagonalCoulombHamiltonian:
         constant = self.constant
 
         def matvec(t):
-            # num_linop @ vec: rotate into the eigenbasis of h, contract, rotate back
-            work = t.clone()
-            _rotate_device(work, vecs_dag, vecs_dag, norb, nelec)
-            result = _device.empty_like(t)
-            _contract_num(work, result, eigs, norb, nelec, accumulate=False)
+            # num_linop @ vec: rotate into the eigenbasis of h, contract (in place: the operator is
+            # diagonal there), rotate back -- one state-sized temporary besides the result
+            result = t.clone()
+            _rotate_device(result, vecs_dag, vecs_dag, norb, nelec)
+            _contract_num(result, result, eigs, norb, nelec, accumulate=False)
             _rotate_device(result, vecs, vecs, norb, nelec)
             # + dc_linop @ vec (accumulate form) + constant * vec
             _contract_dc(t, result, dc_mats, norb, nelec, False, accumulate=True)

@@ -184,6 +184,15 @@ int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const do
 /* out[c, r] = in[r, c]; in is n_rows x n_cols with row stride ld_in, out has row stride ld_out. */
 int ffb_transpose(const void *in_dev, void *out_dev, int64_t n_rows, int64_t n_cols, int64_t ld_in,
                   int64_t ld_out, void *stream);
+/* One rank's side of the distributed transpose of a row-sharded state (no reference counterpart:
+ * SURVEY.md section 8e).  Block d (d < n_dst <= 16) is rows[d] x width[d] complex128 elements, read from
+ * src_dev + src_off[d] with row stride src_ld and stored to dst_dev[d] + dst_off[d] with row stride
+ * dst_ld[d] (all in elements).  dst_dev[d] may point into another GPU's memory mapped over NVLink
+ * (CUDA IPC / symmetric memory): the pack, all-to-all and unpack steps become this one kernel.  The
+ * caller orders it against the peers (a barrier before the buffers are overwritten, one after). */
+int ffb_exchange_blocks(const void *src_dev, int64_t src_ld, int n_dst, const int64_t *rows,
+                        const int64_t *width, const int64_t *src_off, void *const *dst_dev,
+                        const int64_t *dst_off, const int64_t *dst_ld, void *stream);
 /* result_dev[0] = sum conj(x) * y as one complex128 (device scalar, 16 bytes). */
 int ffb_vdot(const void *x_dev, const void *y_dev, int64_t n, void *result_dev, void *stream);
 /* y = alpha * x + beta * y, complex scalars */

@@ -34,6 +34,59 @@ def slater_minors(u, norb, nocc):
     return out
 
 
+def wick_energy(ham, u, nocc_a, nocc_b):
+    """<H> of the determinant U|HF> from its 1-RDM: an O(n^2) closed form."""
+    pa = u[:, :nocc_a] @ u[:, :nocc_a].conj().T
+    pb = u[:, :nocc_b] @ u[:, :nocc_b].conj().T
+    h, (jaa, jab) = np.asarray(ham.one_body_tensor), np.asarray(ham.diag_coulomb_mats)
+    e = ham.constant + np.trace(h @ pa).real + np.trace(h @ pb).real
+    for p_ in (pa, pb):  # same-spin: <n_p n_q> = P_pp P_qq - |P_pq|^2 (p != q), P_pp (p == q)
+        d = np.real(np.diag(p_))
+        nn = np.outer(d, d) - np.abs(p_) ** 2
+        np.fill_diagonal(nn, d)
+        e += 0.5 * np.sum(jaa * nn)
+    da, db = np.real(np.diag(pa)), np.real(np.diag(pb))
+    e += 0.5 * np.sum(jab * (np.outer(da, db) + np.outer(db, da)))
+    return float(e)
+
+
+def run_c5(norb, nelec, dev, world, rank, sync):
+    ham = ffsim.random.random_diagonal_coulomb_hamiltonian(norb, seed=2405)
+    u = ffsim.random.random_unitary(norb, seed=2406)
+    dim = ffsim.dim(norb, nelec)
+    sync()
+    t0 = time.perf_counter()
+    state = ShardedVector.hartree_fock(norb, nelec, device=dev)
+    state = ffsim.apply_orbital_rotation(state, u, norb, nelec, copy=False)
+    sync()
+    prep_ms = (time.perf_counter() - t0) * 1e3
+    linop = ffsim.linear_operator(ham, norb=norb, nelec=nelec)
+    times, energy = [], None
+    for it in range(3):
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        hv = linop @ state
+        energy = state.vdot(hv).real
+        b.record()
+        sync()
+        t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t))
+        del hv
+    want = wick_energy(ham, u, nelec[0], nelec[1])
+    out = {"workload": f"DiagonalCoulombHamiltonian linear_operator energy after orbital rotation, norb={norb} "
+                       f"nelec={list(nelec)}, row-sharded", "n_gpus": world, "dim": dim, "state_GB": dim * 16 / 1e9,
+           "state_preparation_ms": prep_ms, "energy_ms": float(np.median(times[1:])), "times_ms": times,
+           "energy": energy, "energy_closed_form_wick": want, "abs_err": abs(energy - want),
+           "norm": state.norm(), "algorithmic_hbm_bytes_matvec": 240 * dim,
+           "peak_device_GB": torch.cuda.max_memory_allocated() / 1e9}
+    out["algorithmic_TBps_total"] = out["algorithmic_hbm_bytes_matvec"] / (out["energy_ms"] * 1e-3) / 1e12
+    if rank == 0:
+        print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--norb", type=int, default=14)
@@ -41,6 +94,8 @@ def main():
     ap.add_argument("--n-reps", type=int, default=3)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--energy", action="store_true")
+    ap.add_argument("--c5", action="store_true",
+                    help="BASELINE config C5 instead: DiagonalCoulombHamiltonian energy of a rotated determinant")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -62,6 +117,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.c5:
+        run_c5(norb, nelec, dev, world, rank, sync)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # parity of one sharded rotation against the closed form (outer product of Slater minors)
     hf = ShardedVector.hartree_fock(norb, nelec, device=dev)

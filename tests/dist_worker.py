@@ -76,6 +76,10 @@ def main():
         assert err < tol, ("trotter", norb, nelec, err)
     hf = ShardedVector.hartree_fock(8, (4, 4), device=dev)
     assert abs(hf.norm() - 1) < 1e-15
+    if world > 1 and os.environ.get("FFSIM_B200_REPORT_EXCHANGE"):
+        from ffsim_b200 import distributed
+
+        print("exchange=" + ("p2p" if distributed.p2p_available(hf) else "nccl"))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

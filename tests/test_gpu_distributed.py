@@ -1,4 +1,7 @@
-"""Sharded-state GPU tests: world size 1 in-process, world size 2 under torchrun when two GPUs exist."""
+"""Sharded-state GPU tests: world size 1 in-process, world size 2 under torchrun when two GPUs exist.
+
+Both implementations of the redistribution are covered: the peer-memory exchange kernel
+(symmetric memory over NVLink, the default on one box) and NCCL all_to_all_single."""
 
 import os
 import subprocess
@@ -16,14 +19,18 @@ def test_sharded_world_size_1():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
 
 
-def test_sharded_world_size_2_nccl():
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_sharded_world_size_2(exchange):
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    env = dict(os.environ, FFSIM_B200_EXCHANGE=exchange, FFSIM_B200_REPORT_EXCHANGE="1")
     out = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-         "--master-addr", "127.0.0.1", "--master-port", "29711", WORKER],
-        capture_output=True, text=True, timeout=900, cwd=ROOT)
+         "--master-addr", "127.0.0.1", "--master-port", "29711" if exchange == "p2p" else "29712", WORKER],
+        capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2
+    # the worker reports which path it actually took: no silent fallback
+    assert out.stdout.count(f"exchange={exchange}") == 2, out.stdout[-2000:]
