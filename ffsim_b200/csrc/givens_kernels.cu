@@ -246,6 +246,7 @@ __device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const ui
 }
 
 constexpr int kLoadUnroll = 8;
+constexpr int kTilePerThread = 28;  // >= 220 KB / 16 B / 512 threads
 
 template <int W>
 __global__ void __launch_bounds__(512, 1)
@@ -288,38 +289,37 @@ __global__ void __launch_bounds__(512, 1)
       const uint32_t *__restrict__ tab = p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
       const int n_el = R * cols;
       const bool row_major = p.col_stride == 1;  // batch index contiguous in memory
-      // Each element needs its row offset from the (global) tile row table first: all kLoadUnroll
-      // table loads are issued before the first data load, so that a batch costs two memory
-      // latencies instead of 2 * kLoadUnroll (the issue order is the program order).
-      for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
-        int dst[kLoadUnroll], jj[kLoadUnroll];
-        uint32_t trow[kLoadUnroll];
+      // Each element needs its row offset from the (global) tile row table first.  All table loads
+      // of a thread (a 220 KB tile is <= 28 elements per thread at 512 threads) are issued before the
+      // first copy, and the copies are asynchronous (LDGSTS): the whole tile costs two memory
+      // latencies, not two per batch.
+      for (int e_base = 0; e_base < n_el; e_base += kTilePerThread * nthr) {
+        uint32_t trow[kTilePerThread];
 #pragma unroll
-        for (int u = 0; u < kLoadUnroll; ++u) {
-          const int e = e0 + u * nthr;
-          const int ec = e < n_el ? e : 0;
-          int r, j;
-          if (row_major) {
-            r = fast_div(ec, inv_cols);
-            j = ec - r * cols;
-          } else {
-            j = fast_div(ec, inv_R);
-            r = ec - j * R;
+        for (int k = 0; k < kTilePerThread; ++k) {
+          const int e = e_base + tid + k * nthr;
+          const int r = row_major ? fast_div(e, inv_cols) : e - fast_div(e, inv_R) * R;
+          trow[k] = e < n_el ? tab[r] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < kTilePerThread; ++k) {
+          const int e = e_base + tid + k * nthr;
+          if (e < n_el) {
+            int r, j;
+            if (row_major) {
+              r = fast_div(e, inv_cols);
+              j = e - r * cols;
+            } else {
+              j = fast_div(e, inv_R);
+              r = e - j * R;
+            }
+            double2 *dst = tile + r * cols + j;
+            if (j < ncv && !FFB_KNOB(2))
+              cp_async16(dst, data + (long long)(rowbase + trow[k]) * p.row_stride + (col0 + j) * p.col_stride);
+            else
+              *dst = make_double2(0.0, 0.0);
           }
-          dst[u] = e < n_el ? r * cols + j : -1;
-          jj[u] = j;
-          trow[u] = tab[r];
         }
-        double2 v[kLoadUnroll];
-#pragma unroll
-        for (int u = 0; u < kLoadUnroll; ++u) {
-          v[u] = make_double2(0.0, 0.0);
-          if (dst[u] >= 0 && jj[u] < ncv && !FFB_KNOB(2))
-            v[u] = data[(long long)(rowbase + trow[u]) * p.row_stride + (col0 + jj[u]) * p.col_stride];
-        }
-#pragma unroll
-        for (int u = 0; u < kLoadUnroll; ++u)
-          if (dst[u] >= 0) tile[dst[u]] = v[u];
       }
     }
     FFB_TACC(0);
@@ -346,8 +346,8 @@ __global__ void __launch_bounds__(512, 1)
         }
       }
       if (tid == 0) chunk_ctr[0] = nwarp;
-      cp_async_wait_all();
     }
+    cp_async_wait_all();  // the tile and the first offset table
     __syncthreads();
     FFB_TACC(1);
     cached_group = work ? gi : cached_group;
@@ -424,36 +424,43 @@ __global__ void __launch_bounds__(512, 1)
       const uint32_t *__restrict__ tab = p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
       const int n_el = R * cols;
       const bool row_major = p.col_stride == 1;
-      for (int e0 = tid; e0 < n_el; e0 += kLoadUnroll * nthr) {
-        int src[kLoadUnroll], jj[kLoadUnroll];
-        uint32_t grow[kLoadUnroll];
+      for (int e_base = 0; e_base < n_el; e_base += kTilePerThread * nthr) {
+        uint32_t grow[kTilePerThread];
 #pragma unroll
-        for (int u = 0; u < kLoadUnroll; ++u) {
-          const int e = e0 + u * nthr;
-          const int ec = e < n_el ? e : 0;
-          int r, j;
-          if (row_major) {
-            r = fast_div(ec, inv_cols);
-            j = ec - r * cols;
-          } else {
-            j = fast_div(ec, inv_R);
-            r = ec - j * R;
+        for (int k = 0; k < kTilePerThread; ++k) {
+          const int e = e_base + tid + k * nthr;
+          const int r = row_major ? fast_div(e, inv_cols) : e - fast_div(e, inv_R) * R;
+          grow[k] = e < n_el ? rowbase + tab[r] : 0u;
+        }
+        constexpr int kHalf = kTilePerThread / 2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          double2 f[kHalf];
+          if (rowphase) {
+#pragma unroll
+            for (int k = 0; k < kHalf; ++k) {
+              const int e = e_base + tid + (h * kHalf + k) * nthr;
+              f[k] = e < n_el ? rowphase[grow[h * kHalf + k]] : make_double2(1.0, 0.0);
+            }
           }
-          src[u] = (e < n_el && j < ncv && !FFB_KNOB(2)) ? r * cols + j : -1;
-          jj[u] = j;
-          grow[u] = rowbase + tab[r];
-        }
-        double2 f[kLoadUnroll];
-        if (rowphase) {
 #pragma unroll
-          for (int u = 0; u < kLoadUnroll; ++u) f[u] = rowphase[grow[u]];
-        }
-#pragma unroll
-        for (int u = 0; u < kLoadUnroll; ++u) {
-          if (src[u] >= 0) {
-            double2 v = tile[src[u]];
-            if (rowphase) v = make_double2(v.x * f[u].x - v.y * f[u].y, v.x * f[u].y + v.y * f[u].x);
-            data[(long long)grow[u] * p.row_stride + (col0 + jj[u]) * p.col_stride] = v;
+          for (int k = 0; k < kHalf; ++k) {
+            const int e = e_base + tid + (h * kHalf + k) * nthr;
+            if (e < n_el) {
+              int r, j;
+              if (row_major) {
+                r = fast_div(e, inv_cols);
+                j = e - r * cols;
+              } else {
+                j = fast_div(e, inv_R);
+                r = e - j * R;
+              }
+              if (j < ncv && !FFB_KNOB(2)) {
+                double2 v = tile[r * cols + j];
+                if (rowphase) v = make_double2(v.x * f[k].x - v.y * f[k].y, v.x * f[k].y + v.y * f[k].x);
+                data[(long long)grow[h * kHalf + k] * p.row_stride + (col0 + j) * p.col_stride] = v;
+              }
+            }
           }
         }
       }
