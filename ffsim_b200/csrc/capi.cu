@@ -112,7 +112,8 @@ struct DevicePass {
   uint32_t *d_u32 = nullptr;
   uint8_t *d_u8 = nullptr;
   GroupSubDev *d_gsub = nullptr;
-  uint16_t *d_off = nullptr;
+  uint32_t *d_off = nullptr;
+  int blk_cap = 4;  // longest block list of any (group, sub-pass), rounded up to 4 entries
   struct GroupOffsets {
     uint32_t tabrow_off, combo_base_off, combo_low_off, gsub_off;
   };
@@ -141,6 +142,9 @@ int build_device_pass(int norb, int nocc, const PassSchedule &ps, std::unique_pt
   std::vector<uint8_t> u8;
   std::vector<GroupSubDev> gsub;
   const int n_sub = (int)ps.subs.size();
+  auto pad4 = [&]() {  // block lists are staged into shared memory with 16-byte copies
+    while (u32.size() % 4) u32.push_back(0);
+  };
   for (PassGroupHost &G : dp->host.groups) {
     DevicePass::GroupOffsets go;
     go.tabrow_off = (uint32_t)u32.size();
@@ -154,14 +158,19 @@ int build_device_pass(int norb, int nocc, const PassSchedule &ps, std::unique_pt
       GroupSubHost &gs = G.subs[s];
       GroupSubDev d;
       std::memset(&d, 0, sizeof(d));
+      pad4();
       d.blocks_off = (uint32_t)u32.size();
       d.n_seg = gs.n_seg;
+      d.n_blocks = (int)gs.blocks.size();
+      dp->blk_cap = std::max(dp->blk_cap, (d.n_blocks + 3) & ~3);
       for (int k = 0; k < gs.n_seg && k < kMaxSeg; ++k) {
         d.seg[k].mp = gs.seg_mp[k];
         d.seg[k].begin = gs.seg_begin[k];
         d.seg[k].count = gs.seg_count[k];
+        d.seg[k].inv_count = 0xFFFFFFFFu / (unsigned)std::max(1, gs.seg_count[k]) + 1u;
       }
       u32.insert(u32.end(), gs.blocks.begin(), gs.blocks.end());
+      pad4();
       gsub.push_back(d);
       std::vector<uint32_t>().swap(gs.blocks);
     }
@@ -173,7 +182,19 @@ int build_device_pass(int norb, int nocc, const PassSchedule &ps, std::unique_pt
   if ((rc = upload(u32, &dp->d_u32)) != FFB_OK) return rc;
   if ((rc = upload(u8, &dp->d_u8)) != FFB_OK) return rc;
   if ((rc = upload(gsub, &dp->d_gsub)) != FFB_OK) return rc;
-  if ((rc = upload(dp->host.off, &dp->d_off)) != FFB_OK) return rc;
+  // device form of the block-offset tables: byte offsets, every class starting on a 16-byte boundary
+  std::vector<uint32_t> off32((size_t)n_sub * kMaxLowDev * kOffRowDev, 0);
+  for (int s = 0; s < n_sub; ++s) {
+    const int w = ps.subs[s].w;
+    for (int lp = 0; lp < kMaxLow; ++lp)
+      for (int mp = 1; mp < w; ++mp) {
+        const int n = (int)binom(w, mp);
+        for (int t = 0; t < n; ++t)
+          off32[((size_t)s * kMaxLowDev + lp) * kOffRowDev + dev_class_offset(w, mp) + t] =
+              16u * dp->host.off[((size_t)s * kMaxLow + lp) * kOffRow + class_offset(w, mp) + t];
+      }
+  }
+  if ((rc = upload(off32, &dp->d_off)) != FFB_OK) return rc;
   *out = std::move(dp);
   return FFB_OK;
 }
@@ -311,13 +332,15 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     }
     return FFB_OK;
   }
-  const size_t overhead = fused_pass_smem_overhead();
-  size_t budget = std::min<size_t>((size_t)plan->opt.smem_bytes, plan->dev.smem_optin - overhead - 64);
-  const int64_t budget_amps = (int64_t)(budget / 16);
   static thread_local PassParams P;  // 16 KB: keep it off the stack
   for (size_t ip = 0; ip < n_pass; ++ip) {
     DevicePass &dp = *sp.structure->passes[ip];
     const bool last = ip + 1 == n_pass;
+    const size_t overhead = fused_pass_smem_overhead((int)dp.sched.subs.size(), dp.blk_cap);
+    if (overhead + 64 + 1024 > plan->dev.smem_optin)
+      return fail(FFB_EINTERNAL, "pass tables do not fit in shared memory");
+    size_t budget = std::min<size_t>((size_t)plan->opt.smem_bytes, plan->dev.smem_optin - overhead - 64);
+    const int64_t budget_amps = (int64_t)(budget / 16);
     std::memset(&P, 0, sizeof(P));
     P.data = data;
     P.row_stride = row_stride;
@@ -329,6 +352,7 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     P.gsub = dp.d_gsub;
     P.off = dp.d_off;
     P.n_sub = (int)dp.sched.subs.size();
+    P.blk_cap = dp.blk_cap;
     P.n_rot = (int)dp.sched.rot_index.size();
     P.w = dp.sched.subs.empty() ? 2 : dp.sched.subs[0].w;
     if (P.n_sub > kMaxSubPerPass || P.n_rot > kMaxRotPerPass)
@@ -364,7 +388,7 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
       const PassGroupHost &G = dp.host.groups[gi];
       if (!G.has_blocks && !P.rowphase) continue;  // nothing to do for these rows in this pass
       if (ng >= kMaxGroups) return fail(FFB_EINTERNAL, "too many tile groups");
-      int64_t fit = std::max<int64_t>(1, budget_amps / G.R);
+      int64_t fit = std::max<int64_t>(1, budget_amps / (G.R | 1));  // tile columns are G.R | 1 apart
       int64_t cols;
       if (col_stride == 1) {
         cols = fit >= 8 ? std::min<int64_t>(64, fit & ~7ll) : fit;
@@ -389,17 +413,17 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
       L.unit_begin = units;
       L.n_strips = (n_cols + cols - 1) / cols;
       units += L.n_strips * L.n_combos;
-      tile_bytes = std::max(tile_bytes, (size_t)G.R * cols * 16);
+      tile_bytes = std::max(tile_bytes, (size_t)(G.R | 1) * cols * 16);
     }
     P.n_groups = ng;
     P.total_units = units;
     if (units == 0) continue;
     // persistent grid: every CTA resident at once (registers, shared memory and threads counted)
-    const int ctas_per_sm = fused_pass_ctas_per_sm(P.w, plan->opt.threads, tile_bytes);
+    const int ctas_per_sm = fused_pass_ctas_per_sm(P.w, plan->opt.threads, tile_bytes + overhead);
     const int grid = (int)std::min<long long>(units, (long long)plan->dev.sm_count * ctas_per_sm);
     {
       ProfScope prof(kProfFused, 32.0 * (double)dim * (double)n_cols, stream);
-      FFB_CUDA(launch_fused_pass(P, grid, plan->opt.threads, tile_bytes, stream));
+      FFB_CUDA(launch_fused_pass(P, grid, plan->opt.threads, tile_bytes + overhead, stream));
     }
   }
   return FFB_OK;

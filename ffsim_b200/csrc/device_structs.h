@@ -14,20 +14,38 @@ constexpr int kMaxGroups = 33;       // distinct electron counts inside a window
 constexpr int kMaxRotPerPass = 512;  // >= 32*31/2
 constexpr int kMaxSubPerPass = 96;
 constexpr int kMaxLowDev = 16;       // distinct electron counts below a register block
-constexpr int kOffRow = 64;          // u16 entries per row of the block-offset table (2^6 - 2 used)
+constexpr int kOffRow = 64;          // u16 entries per row of the host block-offset table (2^6 - 2 used)
+constexpr int kOffRowDev = 68;       // u32 entries per row of the device table: classes padded to 4 entries
 constexpr int kMaxSeg = 5;           // classes m' = 1..w-1 of a 6-wide register block
+
+// start of class m' inside a device row: every class starts on a 16-byte boundary so that a thread
+// fetches four byte offsets with one shared-memory load
+FFB_HD constexpr int dev_class_offset(int w, int mp) {
+  int off = 0;
+  for (int j = 1; j < mp; ++j) {
+    long long c = 1;
+    for (int i = 1; i <= j; ++i) c = c * (w - j + i) / i;
+    off += ((int)c + 3) & ~3;
+  }
+  return off;
+}
+static_assert(dev_class_offset(6, 5) + 8 <= kOffRowDev, "device offset row too short");
 
 // One class of register blocks inside a (group, sub-pass)
 struct SegDev {
-  int mp;     // electrons inside the register block
-  int begin;  // first block (index into the group's block list for that sub-pass)
-  int count;  // number of blocks
+  int mp;              // electrons inside the register block
+  int begin;           // first block (index into the group's block list for that sub-pass)
+  int count;           // number of blocks
+  unsigned inv_count;  // 0xFFFFFFFF / count + 1 (0 for count == 1)
 };
 struct GroupSubDev {
-  uint32_t blocks_off;  // into PassParams::u32
+  uint32_t blocks_off;  // into PassParams::u32, a multiple of 4 (the list is staged with 16-byte copies)
   int n_seg;
+  int n_blocks;         // length of the block list
+  int pad;
   SegDev seg[kMaxSeg];
 };
+static_assert(sizeof(GroupSubDev) % 16 == 0, "GroupSubDev is copied in 16-byte units");
 struct GroupLaunch {
   int R;                    // tile rows
   int cols;                 // tile columns (chosen at launch)
@@ -64,8 +82,10 @@ struct PassParams {
   const uint32_t *u32;
   const uint8_t *u8;
   const GroupSubDev *gsub;
-  const uint16_t *off;   // [n_sub][kMaxLow][kOffRow]
+  const uint32_t *off;   // [n_sub][kMaxLowDev][kOffRowDev] byte offsets (row offset * 16)
   int n_groups, n_sub, n_rot, w;
+  int blk_cap;           // u32 entries of one block-list staging buffer (longest list, multiple of 4)
+  int pad0;
   long long total_units;
   GroupLaunch g[kMaxGroups];
   SubMeta sub[kMaxSubPerPass];

@@ -85,6 +85,26 @@ __device__ __forceinline__ void zrot(double2 &x, double2 &y, double c, double sr
   y.y = fma(si, xr, fma(-sr, xi, c * yi));
 }
 
+// 16-byte shared-memory accesses by 32-bit shared address
+__device__ __forceinline__ uint4 lds_u4(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u1(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 lds_z(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_z(unsigned addr, double2 v) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+
 // all (x, y) pairs of a W-orbital, M-electron register block for the rotation
 // on block-relative orbitals (Q, Q+1); statically unrolled
 template <int W, int M, int Q, int S = 0>
@@ -99,7 +119,9 @@ __device__ __forceinline__ void rot_block(double2 (&a)[cbinom(W, M)], double c, 
 }
 
 // A run of LEN rotations on block-relative pairs (QHI, QHI+1), (QHI-1, QHI), ...: straight-line
-// code, coefficients read from the constant bank (the pass parameters).
+// code, coefficients read from the constant bank (the pass parameters).  (A shared-memory
+// coefficient table with explicit prefetch was measured 35% slower: the loads compete with the
+// gathers for the LSU, the constant cache does not.)
 template <int W, int M, int QHI, int LEN>
 __device__ __forceinline__ void run_block(double2 (&a)[cbinom(W, M)], const PassParams &p, int r) {
   if constexpr (QHI <= W - 2 && QHI - LEN + 1 >= 0) {
@@ -140,25 +162,22 @@ __device__ __forceinline__ void run_dispatch(double2 (&a)[cbinom(W, M)], const P
 }
 #undef FFB_RUN_CASE
 
-// One register block: gather, rotate, scatter.
+// One register block: gather, rotate, scatter.  `a_addr` is the shared address of the block's base
+// row in the item's tile column; `o_addr` the shared address of the block's byte-offset list (four
+// offsets per 16-byte load; re-read for the scatter so that no address stays live across the math).
 template <int W, int M>
-__device__ __forceinline__ void process_item(double2 *__restrict__ tile, int cols, int col,
-                                             uint32_t entry, const uint16_t *__restrict__ offtab,
-                                             const PassParams &p, int run0, int run1) {
-  constexpr int N = cbinom(W, M);
-  const int base = (int)(entry & 0xFFFFFFu);
-  const uint16_t *o = offtab + (entry >> 24) * kOffRow + cclass_offset(W, M);
+__device__ __forceinline__ void process_item(unsigned a_addr, unsigned o_addr, const PassParams &p,
+                                             int run0, int run1) {
+  constexpr int N = cbinom(W, M), N4 = (N + 3) / 4;
   double2 a[N];
-  unsigned idx2[(N + 1) / 2];  // tile indices, two 16-bit values per register
   FFB_T0();
 #pragma unroll
-  for (int t = 0; t < N; ++t) {
-    const unsigned i = (unsigned)((base + (int)o[t]) * cols + col);
-    a[t] = tile[i];
-    if (t & 1)
-      idx2[t >> 1] |= i << 16;
-    else
-      idx2[t >> 1] = i;
+  for (int t4 = 0; t4 < N4; ++t4) {
+    const uint4 o = lds_u4(o_addr + 16 * t4);
+    a[4 * t4] = lds_z(a_addr + o.x);
+    if (4 * t4 + 1 < N) a[4 * t4 + 1] = lds_z(a_addr + o.y);
+    if (4 * t4 + 2 < N) a[4 * t4 + 2] = lds_z(a_addr + o.z);
+    if (4 * t4 + 3 < N) a[4 * t4 + 3] = lds_z(a_addr + o.w);
   }
   FFB_TACC(3);
   // one dispatch per run; the next run's descriptor is fetched while the current one executes
@@ -171,29 +190,44 @@ __device__ __forceinline__ void process_item(double2 *__restrict__ tile, int col
   }
   FFB_TACC(4);
 #pragma unroll
-  for (int t = 0; t < N; ++t) tile[(t & 1) ? (idx2[t >> 1] >> 16) : (idx2[t >> 1] & 0xFFFFu)] = a[t];
+  for (int t4 = 0; t4 < N4; ++t4) {
+    const uint4 o = lds_u4(o_addr + 16 * t4);
+    sts_z(a_addr + o.x, a[4 * t4]);
+    if (4 * t4 + 1 < N) sts_z(a_addr + o.y, a[4 * t4 + 1]);
+    if (4 * t4 + 2 < N) sts_z(a_addr + o.z, a[4 * t4 + 2]);
+    if (4 * t4 + 3 < N) sts_z(a_addr + o.w, a[4 * t4 + 3]);
+  }
   FFB_TACC(5);
 }
 
 template <int W, int M = 1>
-__device__ __forceinline__ void process_dispatch(int mp, double2 *tile, int cols, int col,
-                                                 uint32_t entry, const uint16_t *offtab,
+__device__ __forceinline__ void process_dispatch(int mp, unsigned a_addr, unsigned o_row_addr,
                                                  const PassParams &p, int run0, int run1) {
   if constexpr (M < W) {
     if (mp == M)
-      process_item<W, M>(tile, cols, col, entry, offtab, p, run0, run1);
+      process_item<W, M>(a_addr, o_row_addr + 4 * dev_class_offset(W, M), p, run0, run1);
     else
-      process_dispatch<W, M + 1>(mp, tile, cols, col, entry, offtab, p, run0, run1);
+      process_dispatch<W, M + 1>(mp, a_addr, o_row_addr, p, run0, run1);
   }
 }
 
-constexpr int kOffTabEntries = kMaxLowDev * kOffRow;  // u16 entries of one sub-pass table
+constexpr int kOffTabEntries = kMaxLowDev * kOffRowDev;  // u32 entries of one sub-pass table
 constexpr int kChunkRow = 8;  // u16 per sub-pass: chunk-prefix of <= kMaxSeg segments, pad, total
 static_assert(kMaxSeg + 1 < kChunkRow, "chunk row too short");
-// shared-memory prefix: two block-offset tables + the group's per-sub-pass block lists + chunk prefixes
-constexpr size_t kGsubBytes = (kMaxSubPerPass * sizeof(GroupSubDev) + 15) / 16 * 16;
-constexpr size_t kFusedSmemOverhead =
-    2 * kOffTabEntries * sizeof(uint16_t) + kGsubBytes + kMaxSubPerPass * kChunkRow * sizeof(uint16_t);
+static_assert(kOffTabEntries % 4 == 0, "offset tables are copied in 16-byte units");
+
+// shared-memory prefix of the kernel: two block-offset tables, the group's per-sub-pass segment
+// descriptors, their chunk prefixes and two block-list staging buffers
+__host__ __device__ inline size_t fused_smem_gsub_off() { return 2 * kOffTabEntries * sizeof(uint32_t); }
+__host__ __device__ inline size_t fused_smem_cend_off(int n_sub) {
+  return fused_smem_gsub_off() + (size_t)n_sub * sizeof(GroupSubDev);
+}
+__host__ __device__ inline size_t fused_smem_blk_off(int n_sub) {
+  return fused_smem_cend_off(n_sub) + (size_t)n_sub * kChunkRow * sizeof(uint16_t);
+}
+__host__ __device__ inline size_t fused_smem_tile_off(int n_sub, int blk_cap) {
+  return fused_smem_blk_off(n_sub) + 2 * (size_t)blk_cap * sizeof(uint32_t);
+}
 
 // 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, no stall at issue
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -216,16 +250,17 @@ struct ChunkWork {
 
 // The g-th chunk of the concatenated (heavy classes first) chunk list of a sub-pass.  `cend` is the
 // sub-pass's row of the chunk-prefix table: cend[k] = chunks in segments 0..k (0xFFFF past the last
-// segment), cend[kChunkRow-1] = total.  One 16-byte shared load finds the segment.
+// segment), cend[kChunkRow-1] = total.  Items of a segment are (column, block) pairs with the block
+// index running fastest: the lanes of a chunk read consecutive block bases.  Everything comes from
+// shared memory (the block list of the sub-pass is staged there one sub-pass ahead).
 __device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const uint16_t *cend,
-                                                 const uint32_t *__restrict__ u32, int g, int lane,
-                                                 int cols, unsigned inv_cols) {
+                                                 const uint32_t *blk, int g, int lane, int cols) {
   ChunkWork w;
   w.entry = 0;
   w.mp = 0;
   w.col = 0;
   const uint4 pk = *reinterpret_cast<const uint4 *>(cend);
-  const int c0 = pk.x & 0xFFFF, c1 = pk.x >> 16, c2 = pk.y & 0xFFFF, c3 = pk.y >> 16, c4 = pk.z & 0xFFFF;
+  const int c0 = pk.x & 0xFFFF, c1 = pk.x >> 16, c2 = pk.y & 0xFFFF, c3 = pk.y >> 16;
   static_assert(kMaxSeg == 5, "fetch_chunk unpacks five segment prefixes");
   if (g >= (int)(pk.w >> 16)) return w;
   int sg = 0, base = 0;
@@ -233,30 +268,31 @@ __device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const ui
   if (g >= c1) sg = 2, base = c1;
   if (g >= c2) sg = 3, base = c2;
   if (g >= c3) sg = 4, base = c3;
-  (void)c4;
-  const SegDev seg = gs.seg[sg];
+  const uint4 sq = *reinterpret_cast<const uint4 *>(&gs.seg[sg]);  // mp, begin, count, inv_count
   const int item = ((g - base) << 5) + lane;
-  if (item < seg.count * cols) {
-    const int blk = fast_div(item, inv_cols);
-    w.col = item - blk * cols;
-    w.mp = seg.mp;
-    w.entry = u32[gs.blocks_off + seg.begin + blk];
+  const int count = (int)sq.z;
+  if (item < count * cols) {
+    const int col = fast_div(item, sq.w);
+    w.col = col;
+    w.mp = (int)sq.x;
+    w.entry = blk[(int)sq.y + item - col * count];
   }
   return w;
 }
 
-constexpr int kLoadUnroll = 8;
 constexpr int kTilePerThread = 28;  // >= 220 KB / 16 B / 512 threads
 
 template <int W>
 __global__ void __launch_bounds__(512, 1)
     fused_pass_kernel(const __grid_constant__ PassParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint16_t *offbuf = reinterpret_cast<uint16_t *>(smem_raw);  // 2 x kOffTabEntries
-  GroupSubDev *gsub_s = reinterpret_cast<GroupSubDev *>(smem_raw + 2 * kOffTabEntries * sizeof(uint16_t));
-  uint16_t *cend_s = reinterpret_cast<uint16_t *>(smem_raw + 2 * kOffTabEntries * sizeof(uint16_t) + kGsubBytes);
-  double2 *tile = reinterpret_cast<double2 *>(smem_raw + kFusedSmemOverhead);
-  __shared__ int chunk_ctr[2];
+  uint32_t *offbuf = reinterpret_cast<uint32_t *>(smem_raw);  // 2 x kOffTabEntries
+  GroupSubDev *gsub_s = reinterpret_cast<GroupSubDev *>(smem_raw + fused_smem_gsub_off());
+  uint16_t *cend_s = reinterpret_cast<uint16_t *>(smem_raw + fused_smem_cend_off(p.n_sub));
+  uint32_t *blkbuf = reinterpret_cast<uint32_t *>(smem_raw + fused_smem_blk_off(p.n_sub));  // 2 x blk_cap
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw + fused_smem_tile_off(p.n_sub, p.blk_cap));
+  const unsigned tile_sa = (unsigned)__cvta_generic_to_shared(tile);
+  const unsigned off_sa = (unsigned)__cvta_generic_to_shared(offbuf);
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -271,18 +307,19 @@ __global__ void __launch_bounds__(512, 1)
     while (gi + 1 < p.n_groups && unit >= p.g[gi + 1].unit_begin) ++gi;
     const GroupLaunch &G = p.g[gi];
     const int cols = G.cols;
-    const unsigned inv_cols = G.inv_cols;
+    const int Rp = G.R | 1;  // column stride of the tile in elements: odd, so columns fall in different banks
 
     FFB_T0();
     {
-      // ---- load the tile.  (The tile geometry is decoded here and again before the store, in a
-      // scope of its own, so that none of it stays in registers across the sub-passes.)
+      // ---- load the tile, column-major: element (row r, column j) at tile[j * Rp + r].  (The tile
+      // geometry is decoded here and again before the store, in a scope of its own, so that none of
+      // it stays in registers across the sub-passes.)
       double2 *__restrict__ data = reinterpret_cast<double2 *>(p.data);
       const long long local = unit - G.unit_begin;
       const long long combo = local / G.n_strips;
       const long long strip = local - combo * G.n_strips;
       const int R = G.R;
-      const unsigned inv_R = G.inv_R;
+      const unsigned inv_R = G.inv_R, inv_cols = G.inv_cols;
       const long long col0 = strip * cols;
       const int ncv = (int)min((long long)cols, p.n_cols - col0);
       const uint32_t rowbase = p.u32[G.combo_base_off + combo];
@@ -313,7 +350,7 @@ __global__ void __launch_bounds__(512, 1)
               j = fast_div(e, inv_R);
               r = e - j * R;
             }
-            double2 *dst = tile + r * cols + j;
+            double2 *dst = tile + j * Rp + r;
             if (j < ncv && !FFB_KNOB(2))
               cp_async16(dst, data + (long long)(rowbase + trow[k]) * p.row_stride + (col0 + j) * p.col_stride);
             else
@@ -325,12 +362,17 @@ __global__ void __launch_bounds__(512, 1)
     FFB_TACC(0);
     const bool work = G.has_blocks && p.n_sub > 0;
     if (work) {
-      for (int e = tid; e < kOffTabEntries / 8; e += nthr)
-        cp_async16(offbuf + 8 * e, p.off + 8 * e);
-      if (cached_group != gi) {  // per-(group, sub-pass) block lists: keep them in shared memory
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.gsub + G.gsub_off);
-        const int n32 = p.n_sub * (int)(sizeof(GroupSubDev) / 4);
-        for (int e = tid; e < n32; e += nthr) reinterpret_cast<uint32_t *>(gsub_s)[e] = src[e];
+      // first sub-pass: block-offset table and block list
+      for (int e = tid; e < kOffTabEntries / 4; e += nthr) cp_async16(offbuf + 4 * e, p.off + 4 * e);
+      {
+        const GroupSubDev &g0 = p.gsub[G.gsub_off];
+        const uint32_t *src = p.u32 + g0.blocks_off;
+        for (int e = tid; 4 * e < g0.n_blocks; e += nthr) cp_async16(blkbuf + 4 * e, src + 4 * e);
+      }
+      if (cached_group != gi) {  // per-(group, sub-pass) segment descriptors: keep them in shared memory
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.gsub + G.gsub_off);
+        const int n16 = p.n_sub * (int)(sizeof(GroupSubDev) / 16);
+        for (int e = tid; e < n16; e += nthr) reinterpret_cast<uint4 *>(gsub_s)[e] = src[e];
         // chunk-prefix rows for this group's column count (read straight from global: the copy
         // above is not visible yet)
         for (int sp = tid; sp < p.n_sub; sp += nthr) {
@@ -345,58 +387,51 @@ __global__ void __launch_bounds__(512, 1)
           row[kChunkRow - 1] = (uint16_t)acc;
         }
       }
-      if (tid == 0) chunk_ctr[0] = nwarp;
     }
-    cp_async_wait_all();  // the tile and the first offset table
+    cp_async_wait_all();  // the tile, the first offset table and the first block list
     __syncthreads();
     FFB_TACC(1);
     cached_group = work ? gi : cached_group;
 
-    // ---- sub-passes
+    // ---- sub-passes.  Chunks are dealt to the warps statically, boustrophedon over the heavy-first
+    // chunk list (round k: chunk k * nwarp + warp, or + nwarp - 1 - warp when k is odd), which
+    // keeps the warps balanced at the barrier without any shared counter.
     if (work) {
-      // chunks 0..nwarp-1 of a sub-pass are owned statically (their descriptors are fetched before
-      // the previous barrier); the rest are handed out through a shared counter, heaviest class
-      // first, which keeps the warps balanced at the barrier
-      ChunkWork cur = fetch_chunk(gsub_s[0], cend_s, p.u32, warp, lane, cols, inv_cols);
       for (int s = 0; s < p.n_sub; ++s) {
-        const uint16_t *offtab = offbuf + (s & 1) * kOffTabEntries;
-        if (s + 1 < p.n_sub) {  // prefetch the next sub-pass's offset table (lands before the barrier)
-          uint16_t *dst = offbuf + ((s + 1) & 1) * kOffTabEntries;
-          const uint16_t *src = p.off + (size_t)(s + 1) * kOffTabEntries;
-          for (int e = tid; e < kOffTabEntries / 8; e += nthr) cp_async16(dst + 8 * e, src + 8 * e);
+        const unsigned offtab_sa = off_sa + (unsigned)((s & 1) * kOffTabEntries * sizeof(uint32_t));
+        const uint32_t *blk = blkbuf + (s & 1) * p.blk_cap;
+        if (s + 1 < p.n_sub) {  // stage the next sub-pass's tables (they land before the barrier)
+          uint32_t *dst = offbuf + ((s + 1) & 1) * kOffTabEntries;
+          const uint32_t *src = p.off + (size_t)(s + 1) * kOffTabEntries;
+          for (int e = tid; e < kOffTabEntries / 4; e += nthr) cp_async16(dst + 4 * e, src + 4 * e);
+          const GroupSubDev &gn = gsub_s[s + 1];
+          uint32_t *bdst = blkbuf + ((s + 1) & 1) * p.blk_cap;
+          const uint32_t *bsrc = p.u32 + gn.blocks_off;
+          for (int e = tid; 4 * e < gn.n_blocks; e += nthr) cp_async16(bdst + 4 * e, bsrc + 4 * e);
         }
         const GroupSubDev &gs = gsub_s[s];
         const uint16_t *cend = cend_s + s * kChunkRow;
         const int run0 = p.sub[s].run_begin, run1 = p.sub[s].run_end;
         const int n_chunks = cend[kChunkRow - 1];
-        int *ctr = &chunk_ctr[s & 1];
-        if (tid == 0) chunk_ctr[(s + 1) & 1] = nwarp;
         int g = warp;
-        while (true) {
-          const bool mine = g < n_chunks;
-          int g_next = n_chunks;
-          if (mine) {
-            if (lane == 0) g_next = atomicAdd(ctr, 1);
-            g_next = __shfl_sync(0xffffffffu, g_next, 0);
-          }
+        ChunkWork cur = fetch_chunk(gs, cend, blk, g, lane, cols);
+        for (int k = 1; g < n_chunks; ++k) {
+          const int g_next = k * nwarp + ((k & 1) ? nwarp - 1 - warp : warp);
           ChunkWork nxt;
-          if (g_next < n_chunks) {
-            nxt = fetch_chunk(gs, cend, p.u32, g_next, lane, cols, inv_cols);
-          } else if (s + 1 < p.n_sub) {
-            nxt = fetch_chunk(gsub_s[s + 1], cend + kChunkRow, p.u32, warp, lane, cols, inv_cols);
-          } else {
-            nxt.entry = 0;
-            nxt.mp = 0;
-            nxt.col = 0;
-          }
+          nxt.entry = 0;
+          nxt.mp = 0;
+          nxt.col = 0;
+          if (g_next < n_chunks) nxt = fetch_chunk(gs, cend, blk, g_next, lane, cols);
           FFB_TACC(2);
-          if (mine && cur.mp && !FFB_KNOB(8))
-            process_dispatch<W>(cur.mp, tile, cols, cur.col, cur.entry, offtab, p, run0, run1);
+          if (cur.mp && !FFB_KNOB(8)) {
+            const unsigned a_addr = tile_sa + ((unsigned)(cur.col * Rp + (int)(cur.entry & 0xFFFFFFu)) << 4);
+            const unsigned o_row = offtab_sa + (cur.entry >> 24) * (unsigned)(kOffRowDev * sizeof(uint32_t));
+            process_dispatch<W>(cur.mp, a_addr, o_row, p, run0, run1);
+          }
 #ifdef FFB_DEBUG_TIMING
           _t0 = clock64();
 #endif
           cur = nxt;
-          if (g_next >= n_chunks) break;
           g = g_next;
         }
         cp_async_wait_all();
@@ -417,7 +452,7 @@ __global__ void __launch_bounds__(512, 1)
       const long long combo = local / G.n_strips;
       const long long strip = local - combo * G.n_strips;
       const int R = G.R;
-      const unsigned inv_R = G.inv_R;
+      const unsigned inv_R = G.inv_R, inv_cols = G.inv_cols;
       const long long col0 = strip * cols;
       const int ncv = (int)min((long long)cols, p.n_cols - col0);
       const uint32_t rowbase = p.u32[G.combo_base_off + combo];
@@ -456,7 +491,7 @@ __global__ void __launch_bounds__(512, 1)
                 r = e - j * R;
               }
               if (j < ncv && !FFB_KNOB(2)) {
-                double2 v = tile[r * cols + j];
+                double2 v = tile[j * Rp + r];
                 if (rowphase) v = make_double2(v.x * f[k].x - v.y * f[k].y, v.x * f[k].y + v.y * f[k].x);
                 data[(long long)grow[h * kHalf + k] * p.row_stride + (col0 + j) * p.col_stride] = v;
               }
@@ -489,7 +524,7 @@ static cudaError_t launch_w(const PassParams &p, int grid, int threads, size_t s
   return cudaGetLastError();
 }
 
-size_t fused_pass_smem_overhead() { return kFusedSmemOverhead; }
+size_t fused_pass_smem_overhead(int n_sub, int blk_cap) { return fused_smem_tile_off(n_sub, blk_cap); }
 
 template <int W>
 static int occupancy_w(int threads, size_t smem) {
@@ -504,8 +539,7 @@ static int occupancy_w(int threads, size_t smem) {
 
 // CTAs of the fused kernel that are resident on one SM at this block size and tile size
 // (registers, shared memory and thread limits all counted).
-int fused_pass_ctas_per_sm(int w, int threads, size_t tile_bytes) {
-  const size_t smem = tile_bytes + fused_pass_smem_overhead();
+int fused_pass_ctas_per_sm(int w, int threads, size_t smem) {
   switch (w) {
     case 2: return occupancy_w<2>(threads, smem);
     case 3: return occupancy_w<3>(threads, smem);
@@ -530,9 +564,8 @@ void read_phase_cycles(unsigned long long *out, int reset) {
 }
 #endif
 
-cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t tile_bytes,
+cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t smem,
                               cudaStream_t stream) {
-  size_t smem = tile_bytes + fused_pass_smem_overhead();
   switch (p.w) {
     case 2: return launch_w<2>(p, grid, threads, smem, stream);
     case 3: return launch_w<3>(p, grid, threads, smem, stream);

@@ -11,9 +11,11 @@ struct PhaseList {  // per-orbital phases passed by value
   double re[32], im[32];
 };
 
-size_t fused_pass_smem_overhead();
-int fused_pass_ctas_per_sm(int w, int threads, size_t tile_bytes);
-cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t tile_bytes,
+// shared memory the fused kernel needs besides the tile: offset tables, segment descriptors of
+// `n_sub` sub-passes and two block-list staging buffers of `blk_cap` entries
+size_t fused_pass_smem_overhead(int n_sub, int blk_cap);
+int fused_pass_ctas_per_sm(int w, int threads, size_t smem_bytes);
+cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t smem_bytes,
                               cudaStream_t stream);
 cudaError_t launch_givens_single(void *vec, long long ld, long long dim_b, double c, double sr,
                                  double si, const unsigned long long *s1,

@@ -53,7 +53,7 @@ for k in range(n):
             by_line_stall[lines[k]][h[6:]] += v
 src = open("/root/repo/ffsim_b200/csrc/givens_kernels.cu").read().split("\n")
 print(f"total samples {ts} instructions {ti}")
-for line, s in by_line_smp.most_common(28):
+for line, s in by_line_smp.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 28):
     top = ", ".join(f"{k}:{100*v/max(s,1):.0f}%" for k, v in by_line_stall[line].most_common(3))
     text = src[line - 1].strip()[:70] if line and line <= len(src) else ""
     print(f"{line:5d} smp {100*s/ts:5.1f}% inst {100*by_line_inst[line]/ti:5.1f}%  [{top}]  {text}")
