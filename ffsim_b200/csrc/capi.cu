@@ -388,7 +388,7 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
       const PassGroupHost &G = dp.host.groups[gi];
       if (!G.has_blocks && !P.rowphase) continue;  // nothing to do for these rows in this pass
       if (ng >= kMaxGroups) return fail(FFB_EINTERNAL, "too many tile groups");
-      int64_t fit = std::max<int64_t>(1, budget_amps / (G.R | 1));  // tile columns are G.R | 1 apart
+      int64_t fit = std::max<int64_t>(1, budget_amps / (G.R + 7));  // tile columns are up to R + 7 apart
       int64_t cols;
       if (col_stride == 1) {
         cols = fit >= 8 ? std::min<int64_t>(64, fit & ~7ll) : fit;
@@ -402,6 +402,7 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
       GroupLaunch &L = P.g[ng++];
       L.R = G.R;
       L.cols = (int)cols;
+      L.Rp = tile_col_stride(G.R, (int)cols);
       L.inv_cols = 0xFFFFFFFFu / (unsigned)cols + 1u;
       L.inv_R = 0xFFFFFFFFu / (unsigned)G.R + 1u;
       L.n_combos = (int)G.combo_base.size();
@@ -413,7 +414,7 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
       L.unit_begin = units;
       L.n_strips = (n_cols + cols - 1) / cols;
       units += L.n_strips * L.n_combos;
-      tile_bytes = std::max(tile_bytes, (size_t)(G.R | 1) * cols * 16);
+      tile_bytes = std::max(tile_bytes, (size_t)L.Rp * cols * 16);
     }
     P.n_groups = ng;
     P.total_units = units;

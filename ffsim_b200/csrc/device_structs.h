@@ -46,8 +46,17 @@ struct GroupSubDev {
   SegDev seg[kMaxSeg];
 };
 static_assert(sizeof(GroupSubDev) % 16 == 0, "GroupSubDev is copied in 16-byte units");
+// Column stride (in elements) of the shared-memory tile, which is stored column-major.  The stride
+// is chosen modulo 8 (eight 16-byte bank groups) so that the 16-byte accesses of a quarter-warp
+// that walks the tile in memory order (row, then column fastest: the alpha-side load and store)
+// fall in eight different bank groups: stride = cols (mod 8) for odd cols, 8 / cols for 2, 4, 8.
+FFB_HD constexpr int tile_col_stride(int R, int cols) {
+  const int want = (cols & 1) ? (cols & 7) : (cols == 2 ? 4 : (cols == 4 ? 2 : 1));
+  return R + ((want - R) & 7);
+}
 struct GroupLaunch {
   int R;                    // tile rows
+  int Rp;                   // column stride of the tile, tile_col_stride(R, cols)
   int cols;                 // tile columns (chosen at launch)
   int n_combos;
   int has_blocks;

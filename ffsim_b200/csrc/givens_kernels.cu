@@ -280,10 +280,13 @@ __device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const ui
   return w;
 }
 
-constexpr int kTilePerThread = 28;  // >= 220 KB / 16 B / 512 threads
+#ifndef FFB_TPB
+#define FFB_TPB 512  // CTA size the fused kernel is compiled for (registers per thread = 64K / FFB_TPB)
+#endif
+constexpr int kTilePerThread = (14336 + FFB_TPB - 1) / FFB_TPB;  // >= 220 KB / 16 B / CTA size (28 at 512 threads)
 
 template <int W>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(FFB_TPB, 1)
     fused_pass_kernel(const __grid_constant__ PassParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t *offbuf = reinterpret_cast<uint32_t *>(smem_raw);  // 2 x kOffTabEntries
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(512, 1)
     while (gi + 1 < p.n_groups && unit >= p.g[gi + 1].unit_begin) ++gi;
     const GroupLaunch &G = p.g[gi];
     const int cols = G.cols;
-    const int Rp = G.R | 1;  // column stride of the tile in elements: odd, so columns fall in different banks
+    const int Rp = G.Rp;  // column stride of the tile in elements (see tile_col_stride)
 
     FFB_T0();
     {

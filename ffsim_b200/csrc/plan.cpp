@@ -304,6 +304,30 @@ PassTablesHost build_pass_tables(int norb, int nocc, const PassSchedule &pass) {
           }
         }
         int count = (int)gs.blocks.size() - begin;
+        // Order the class's blocks so that any eight consecutive ones (a quarter-warp: one
+        // shared-memory wavefront of 16-byte accesses) start on rows that differ modulo 8, i.e. in
+        // different bank groups: blocks with the same l' share their offset list, so the whole gather
+        // and scatter of such a group is conflict-free.  (Any order is valid: blocks are disjoint.)
+        if (count > 8) {
+          std::vector<uint32_t> seg(gs.blocks.begin() + begin, gs.blocks.end());
+          std::vector<std::vector<uint32_t>> bucket((size_t)kMaxLow * 8);
+          for (uint32_t e : seg) bucket[(size_t)(e >> 24) * 8 + (e & 7u)].push_back(e);
+          size_t pos = (size_t)begin;
+          int res = 0;  // the residue cycle runs on across l' groups
+          for (int lp = 0; lp < kMaxLow; ++lp) {
+            size_t idx[8] = {0, 0, 0, 0, 0, 0, 0, 0}, left = 0;
+            for (int r = 0; r < 8; ++r) left += bucket[(size_t)lp * 8 + r].size();
+            while (left > 0) {
+              const std::vector<uint32_t> &b = bucket[(size_t)lp * 8 + res];
+              if (idx[res] < b.size()) {
+                gs.blocks[pos++] = b[idx[res]++];
+                --left;
+              }
+              res = (res + 1) & 7;
+            }
+          }
+          assert(pos == gs.blocks.size());
+        }
         if (count > 0) {
           gs.seg_mp[gs.n_seg] = mp;
           gs.seg_begin[gs.n_seg] = begin;
