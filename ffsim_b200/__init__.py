@@ -15,8 +15,13 @@ from ffsim_b200.hamiltonians import DiagonalCoulombHamiltonian, DoubleFactorized
 from ffsim_b200.init_cache import init_cache
 from ffsim_b200.protocols import apply_unitary, linear_operator
 from ffsim_b200.states import dim, dims, hartree_fock_state
-from ffsim_b200.trotter import simulate_trotter_diag_coulomb_split_op, simulate_trotter_double_factorized
-from ffsim_b200.variational import UCJOpSpinBalanced
+from ffsim_b200.trotter import (
+    qdrift_probabilities,
+    simulate_qdrift_double_factorized,
+    simulate_trotter_diag_coulomb_split_op,
+    simulate_trotter_double_factorized,
+)
+from ffsim_b200.variational import UCJOpSpinBalanced, UCJOpSpinless, UCJOpSpinUnbalanced
 
 __version__ = "0.1.0"
 
@@ -24,6 +29,8 @@ __all__ = [
     "DiagonalCoulombHamiltonian",
     "DoubleFactorizedHamiltonian",
     "UCJOpSpinBalanced",
+    "UCJOpSpinUnbalanced",
+    "UCJOpSpinless",
     "apply_diag_coulomb_evolution",
     "apply_num_op_sum_evolution",
     "apply_orbital_rotation",
@@ -39,7 +46,9 @@ __all__ = [
     "linalg",
     "linear_operator",
     "num_op_sum_linop",
+    "qdrift_probabilities",
     "random",
+    "simulate_qdrift_double_factorized",
     "simulate_trotter_diag_coulomb_split_op",
     "simulate_trotter_double_factorized",
 ]

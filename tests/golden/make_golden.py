@@ -39,6 +39,7 @@ from ffsim.states.dimensions import dim as ref_dim  # noqa: E402
 from ffsim.states.slater import hartree_fock_state  # noqa: E402
 from ffsim.trotter.diagonal_coulomb_split_op import simulate_trotter_diag_coulomb_split_op  # noqa: E402
 from ffsim.trotter.double_factorized import simulate_trotter_double_factorized  # noqa: E402
+from ffsim.trotter.qdrift import simulate_qdrift_double_factorized  # noqa: E402
 
 CASES: dict[str, dict] = {}
 NONE = np.zeros((0,))  # stands for a `None` member
@@ -217,6 +218,50 @@ def main():
             order=1, n_steps=2, one_body_tensor=ham.one_body_tensor, diag_coulomb_mats=ham.diag_coulomb_mats,
             constant=ham.constant,
             expected=simulate_trotter_diag_coulomb_split_op(vec, ham, 0.2, norb=norb, nelec=nelec, n_steps=2, order=1))
+
+    # ---- SURVEY.md section 8f rows (appended: the cases above keep their random streams) ----
+    # UCJOpSpinUnbalanced (variational/ucj_spin_unbalanced.py:705): per-spin rotations, J_ab not symmetric
+    for norb, nelec, n_reps, final in [(4, (2, 2), 2, True), (5, (3, 2), 2, False), (6, (2, 4), 1, True)]:
+        op = rr.random_ucj_op_spin_unbalanced(norb, n_reps=n_reps, with_final_orbital_rotation=final, seed=rng)
+        vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}_L{n_reps}"
+        add(f"ucj_unbalanced/{tag}", kind="ucj_unbalanced", norb=norb, nelec=nelec, vec=vec,
+            diag_coulomb_mats=op.diag_coulomb_mats, orbital_rotations=op.orbital_rotations,
+            final_orbital_rotation=opt(op.final_orbital_rotation),
+            expected=apply_unitary(vec, op, norb=norb, nelec=nelec))
+    # UCJOpSpinless (variational/ucj_spinless.py:456): integer nelec and pair nelec
+    for norb, nelec, n_reps, final in [(5, 2, 2, True), (6, 3, 1, False), (4, (2, 1), 2, True), (5, (2, 2), 1, False)]:
+        op = rr.random_ucj_op_spinless(norb, n_reps=n_reps, with_final_orbital_rotation=final, seed=rng)
+        vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng)
+        tag = f"{norb}_{nelec}_L{n_reps}" if isinstance(nelec, int) else f"{norb}_{nelec[0]}_{nelec[1]}_L{n_reps}"
+        add(f"ucj_spinless/{tag}", kind="ucj_spinless", norb=norb, nelec=nelec, vec=vec,
+            diag_coulomb_mats=op.diag_coulomb_mats, orbital_rotations=op.orbital_rotations,
+            final_orbital_rotation=opt(op.final_orbital_rotation),
+            expected=apply_unitary(vec, op, norb=norb, nelec=nelec))
+    # DoubleFactorizedHamiltonian._linear_operator_ (hamiltonians/double_factorized_hamiltonian.py:244)
+    for norb, nelec, rank, z in [(4, (2, 2), 3, False), (5, (3, 2), 4, True)]:
+        ham = rr.random_double_factorized_hamiltonian(norb, rank=rank, z_representation=z, seed=rng)
+        vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}_r{rank}_{'z' if z else 'num'}"
+        add(f"df_hamiltonian/matvec_{tag}", kind="df_matvec", norb=norb, nelec=nelec, vec=vec, z=z,
+            one_body_tensor=ham.one_body_tensor, diag_coulomb_mats=ham.diag_coulomb_mats,
+            orbital_rotations=ham.orbital_rotations, constant=ham.constant,
+            expected=linear_operator(ham, norb=norb, nelec=nelec) @ vec)
+    # simulate_qdrift_double_factorized (trotter/qdrift.py:23): sampling order, both schedules
+    for norb, nelec, rank, z, symmetric, probs, n_steps, n_samples, seed in [
+        (4, (2, 2), 3, False, False, "norm", 4, 1, 4101), (4, (2, 2), 3, False, True, "norm", 3, 2, 4102),
+        (5, (2, 3), 4, True, False, "uniform", 5, 1, 4103), (4, (1, 2), 2, False, True, "uniform", 2, 1, 4104),
+    ]:
+        ham = rr.random_double_factorized_hamiltonian(norb, rank=rank, z_representation=z, seed=rng)
+        vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}_r{rank}_{'z' if z else 'num'}_{'sym' if symmetric else 'plain'}_{probs}"
+        add(f"qdrift/{tag}", kind="qdrift", norb=norb, nelec=nelec, vec=vec, time=0.3, z=z, symmetric=symmetric,
+            probabilities=np.array(list(probs.encode())), n_steps=n_steps, n_samples=n_samples, seed=seed,
+            one_body_tensor=ham.one_body_tensor, diag_coulomb_mats=ham.diag_coulomb_mats,
+            orbital_rotations=ham.orbital_rotations, constant=ham.constant,
+            expected=simulate_qdrift_double_factorized(vec, ham, 0.3, norb=norb, nelec=nelec, n_steps=n_steps,
+                                                       symmetric=symmetric, probabilities=probs,
+                                                       n_samples=n_samples, seed=seed))
 
     flat = {}
     for name, arrays in CASES.items():

@@ -394,6 +394,64 @@ def test_double_factorized_hamiltonian_linear_operator():
         assert np.linalg.norm(got - want) <= TOL * np.linalg.norm(want)
 
 
+# ------------------------------------------------------------------ SURVEY.md 8f rows
+@pytest.mark.parametrize("norb, nelec", [(6, (3, 2)), (7, (2, 4))])
+def test_ucj_spin_unbalanced_and_spinless(norb, nelec):
+    rng = np.random.default_rng(51)
+    n_reps = 2
+    mats3 = np.stack([np.stack([rand.random_real_symmetric_matrix(norb, seed=rng), rng.standard_normal((norb, norb)),
+                                rand.random_real_symmetric_matrix(norb, seed=rng)]) for _ in range(n_reps)])
+    rots2 = np.stack([np.stack([rand.random_unitary(norb, seed=rng), rand.random_unitary(norb, seed=rng)])
+                      for _ in range(n_reps)])
+    final2 = np.stack([rand.random_unitary(norb, seed=rng), rand.random_unitary(norb, seed=rng)])
+    vec = _state(norb, nelec, rng)
+    for final in (None, final2):
+        op = ffsim.UCJOpSpinUnbalanced(mats3, rots2, final_orbital_rotation=final)
+        got = ffsim.apply_unitary(vec, op, norb=norb, nelec=nelec)
+        want = models.ucj_spin_unbalanced_apply(vec, mats3, rots2, final, norb, nelec)
+        assert rel_err(got, want) <= TOL
+    # spinless operator on a spinful state and on a spinless one
+    op = ffsim.UCJOpSpinless(mats3[:, 0], rots2[:, 0], final_orbital_rotation=final2[0])
+    got = ffsim.apply_unitary(vec, op, norb=norb, nelec=nelec)
+    assert rel_err(got, models.ucj_spinless_apply(vec, mats3[:, 0], rots2[:, 0], final2[0], norb, nelec)) <= TOL
+    nocc = nelec[0]
+    vec1 = rand.random_state_vector(math.comb(norb, nocc), seed=rng)
+    got = ffsim.apply_unitary(vec1, op, norb=norb, nelec=nocc)
+    assert rel_err(got, models.ucj_spinless_apply(vec1, mats3[:, 0], rots2[:, 0], final2[0], norb, nocc)) <= TOL
+
+
+def test_qdrift_double_factorized():
+    import torch
+
+    norb, nelec = 5, (2, 3)
+    ham = ffsim.random.random_double_factorized_hamiltonian(norb, rank=3, seed=61)
+    vec = _state(norb, nelec, np.random.default_rng(62))
+    args = (ham.one_body_tensor, ham.diag_coulomb_mats, ham.orbital_rotations, False)
+    probs = np.array([0.1, 0.2, 0.3, 0.4])
+    for symmetric in (False, True):
+        for p in ("norm", "uniform", probs):
+            got = ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, n_steps=6,
+                                                          symmetric=symmetric, probabilities=p, n_samples=3, seed=7)
+            want = models.simulate_qdrift_double_factorized(vec, *args, 0.4, norb=norb, nelec=nelec, n_steps=6,
+                                                            symmetric=symmetric, probabilities=p, n_samples=3, seed=7)
+            assert got.shape == (3, vec.size) and rel_err(got, want) <= TOL
+    assert np.array_equal(probs, [0.1, 0.2, 0.3, 0.4]), "the caller's probabilities must not be modified"
+    # zero steps / zero time return copies of the input; CUDA tensor in -> CUDA tensor out
+    out = ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, n_steps=0)
+    assert np.array_equal(out, vec) and out is not vec
+    dev = torch.from_numpy(vec).cuda()
+    out = ffsim.simulate_qdrift_double_factorized(dev, ham, 0.4, norb=norb, nelec=nelec, n_steps=3, seed=9)
+    want = models.simulate_qdrift_double_factorized(vec, *args, 0.4, norb=norb, nelec=nelec, n_steps=3, seed=9)
+    assert out.is_cuda and torch.equal(dev.cpu(), torch.from_numpy(vec)) and rel_err(out.cpu().numpy(), want) <= TOL
+    with pytest.raises(ValueError, match="n_steps"):
+        ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, n_steps=-1)
+    with pytest.raises(ValueError, match="n_samples"):
+        ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, n_samples=0)
+    with pytest.raises(NotImplementedError):
+        ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, probabilities="optimal",
+                                                one_rdm=np.eye(2 * norb))
+
+
 # ------------------------------------------------------------------ BASELINE shapes: properties
 
 def test_c2_shape_against_c_oracle_and_properties():

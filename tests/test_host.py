@@ -184,3 +184,103 @@ def test_c_restatement_matches_numpy_oracle(norb, nelec):
         np.testing.assert_allclose(
             cref.apply_diag_coulomb_evolution(v, mats, 0.3, norb, nelec, z_representation=z),
             gates.apply_diag_coulomb_evolution(v, mats, 0.3, norb, nelec, z_representation=z), atol=1e-13)
+
+
+# ----------------------------------------------------------------------------- host logic
+def _unitaries(shape, seed):
+    rng = np.random.default_rng(seed)
+    n = shape[-1]
+    out = np.empty(shape, dtype=complex)
+    for idx in np.ndindex(*shape[:-2]):
+        out[idx] = rand.random_unitary(n, seed=rng)
+    return out
+
+
+def test_ucj_spin_unbalanced_validation_errors():
+    import ffsim_b200 as ffsim
+
+    norb, n_reps = 4, 2
+    rng = np.random.default_rng(5)
+    mats = np.stack([np.stack([rand.random_real_symmetric_matrix(norb, seed=rng), rng.standard_normal((norb, norb)),
+                               rand.random_real_symmetric_matrix(norb, seed=rng)]) for _ in range(n_reps)])
+    rots = _unitaries((n_reps, 2, norb, norb), 6)
+    op = ffsim.UCJOpSpinUnbalanced(mats, rots, final_orbital_rotation=rots[0])  # J_ab need not be symmetric
+    assert (op.norb, op.n_reps) == (norb, n_reps)
+    with pytest.raises(ValueError, match="shape"):
+        ffsim.UCJOpSpinUnbalanced(mats[:, :2], rots)
+    with pytest.raises(ValueError, match="shape"):
+        ffsim.UCJOpSpinUnbalanced(mats, rots[:, 0])
+    with pytest.raises(ValueError, match="shape"):
+        ffsim.UCJOpSpinUnbalanced(mats, rots, final_orbital_rotation=rots[0, 0])
+    with pytest.raises(ValueError, match="first dimension"):
+        ffsim.UCJOpSpinUnbalanced(mats, rots[:1])
+    with pytest.raises(ValueError, match="unitary"):
+        ffsim.UCJOpSpinUnbalanced(mats, 1.1 * rots)
+    with pytest.raises(ValueError, match="unitary"):
+        ffsim.UCJOpSpinUnbalanced(mats, rots, final_orbital_rotation=1.1 * rots[0])
+    bad = mats.copy()
+    bad[1, 2, 0, 1] += 1.0
+    with pytest.raises(ValueError, match="symmetric"):
+        ffsim.UCJOpSpinUnbalanced(bad, rots)
+    ffsim.UCJOpSpinUnbalanced(bad, rots, validate=False)
+    # an integer nelec is not supported by this operator: apply_unitary reports it (apply_unitary_protocol.py:76-88)
+    with pytest.raises(TypeError):
+        ffsim.apply_unitary(np.zeros(6, dtype=complex), op, norb=norb, nelec=2)
+
+
+def test_ucj_spinless_validation_errors():
+    import ffsim_b200 as ffsim
+
+    norb, n_reps = 4, 2
+    rng = np.random.default_rng(7)
+    mats = np.stack([rand.random_real_symmetric_matrix(norb, seed=rng) for _ in range(n_reps)])
+    rots = _unitaries((n_reps, norb, norb), 8)
+    op = ffsim.UCJOpSpinless(mats, rots, final_orbital_rotation=rots[1])
+    assert (op.norb, op.n_reps) == (norb, n_reps)
+    with pytest.raises(ValueError, match="shape"):
+        ffsim.UCJOpSpinless(mats[0], rots)
+    with pytest.raises(ValueError, match="shape"):
+        ffsim.UCJOpSpinless(mats, rots[0])
+    with pytest.raises(ValueError, match="shape"):
+        ffsim.UCJOpSpinless(mats, rots, final_orbital_rotation=rots)
+    with pytest.raises(ValueError, match="first dimension"):
+        ffsim.UCJOpSpinless(mats[:1], rots)
+    with pytest.raises(ValueError, match="unitary"):
+        ffsim.UCJOpSpinless(mats, 0.9 * rots)
+    bad = mats.copy()
+    bad[0, 0, 1] += 1.0
+    with pytest.raises(ValueError, match="symmetric"):
+        ffsim.UCJOpSpinless(bad, rots)
+    ffsim.UCJOpSpinless(bad, rots, validate=False)
+
+
+@pytest.mark.parametrize("z_rep", [False, True])
+@pytest.mark.parametrize("rank_one", [False, True])
+def test_qdrift_probabilities_match_oracle(z_rep, rank_one):
+    """Host arithmetic of python/ffsim/trotter/qdrift.py:244-455 ("norm" exact and loose branches, "uniform")."""
+    import ffsim_b200 as ffsim
+
+    norb, nelec, rank = 5, (3, 2), 4
+    rng = np.random.default_rng(11)
+    one_body = rand.random_hermitian(norb, seed=rng) if hasattr(rand, "random_hermitian") else None
+    if one_body is None:
+        m = rng.standard_normal((norb, norb)) + 1j * rng.standard_normal((norb, norb))
+        one_body = m + m.T.conj()
+    if rank_one:
+        vs = rng.standard_normal((rank, norb))
+        mats = np.stack([np.outer(v, v) for v in vs])
+    else:
+        mats = np.stack([rand.random_real_symmetric_matrix(norb, seed=rng) for _ in range(rank)])
+    rots = _unitaries((rank, norb, norb), 12)
+    ham = ffsim.DoubleFactorizedHamiltonian(one_body, mats, rots, constant=0.5, z_representation=z_rep)
+    for method in ("norm", "uniform"):
+        got = ffsim.qdrift_probabilities(ham, method, nelec=nelec)
+        want = models.qdrift_probabilities(one_body, mats, z_rep, method, nelec)
+        assert got.shape == (rank + 1,) and abs(got.sum() - 1) < 1e-14
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+    with pytest.raises(ValueError, match="nelec"):
+        ffsim.qdrift_probabilities(ham, "norm")
+    with pytest.raises(ValueError, match="one_rdm"):
+        ffsim.qdrift_probabilities(ham, "optimal")
+    with pytest.raises(ValueError, match="Unsupported"):
+        ffsim.qdrift_probabilities(ham, "nonsense")

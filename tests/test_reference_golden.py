@@ -85,6 +85,26 @@ class OracleAPI:
             vec, c["one_body_tensor"], c["diag_coulomb_mats"], float(c["constant"]), float(c["time"]), norb=norb,
             nelec=nelec, n_steps=int(c["n_steps"]), order=int(c["order"]))
 
+    def ucj_unbalanced(self, vec, c, norb, nelec):
+        return self.m.ucj_spin_unbalanced_apply(vec, c["diag_coulomb_mats"], c["orbital_rotations"],
+                                                opt(c["final_orbital_rotation"]), norb, nelec)
+
+    def ucj_spinless(self, vec, c, norb, nelec):
+        return self.m.ucj_spinless_apply(vec, c["diag_coulomb_mats"], c["orbital_rotations"],
+                                         opt(c["final_orbital_rotation"]), norb, nelec)
+
+    def df_matvec(self, vec, c, norb, nelec):
+        return self.m.double_factorized_hamiltonian_matvec(
+            vec, c["one_body_tensor"], c["diag_coulomb_mats"], c["orbital_rotations"], float(c["constant"]),
+            bool(c["z"]), norb, nelec)
+
+    def qdrift(self, vec, c, norb, nelec):
+        return self.m.simulate_qdrift_double_factorized(
+            vec, c["one_body_tensor"], c["diag_coulomb_mats"], c["orbital_rotations"], bool(c["z"]), float(c["time"]),
+            norb=norb, nelec=nelec, n_steps=int(c["n_steps"]), symmetric=bool(c["symmetric"]),
+            probabilities=bytes(c["probabilities"].astype(np.uint8)).decode(), n_samples=int(c["n_samples"]),
+            seed=int(c["seed"]))
+
 
 class CudaAPI:
     """ffsim_b200: the public drop-in API over the CUDA library."""
@@ -120,6 +140,28 @@ class CudaAPI:
         return self.f.simulate_trotter_diag_coulomb_split_op(vec, self._dc(c), float(c["time"]), norb=norb, nelec=nelec,
                                                              n_steps=int(c["n_steps"]), order=int(c["order"]))
 
+    def ucj_unbalanced(self, vec, c, norb, nelec):
+        op = self.f.UCJOpSpinUnbalanced(c["diag_coulomb_mats"], c["orbital_rotations"],
+                                        opt(c["final_orbital_rotation"]))
+        return self.f.apply_unitary(vec, op, norb=norb, nelec=nelec)
+
+    def ucj_spinless(self, vec, c, norb, nelec):
+        op = self.f.UCJOpSpinless(c["diag_coulomb_mats"], c["orbital_rotations"], opt(c["final_orbital_rotation"]))
+        return self.f.apply_unitary(vec, op, norb=norb, nelec=nelec)
+
+    def _df(self, c):
+        return self.f.DoubleFactorizedHamiltonian(c["one_body_tensor"], c["diag_coulomb_mats"], c["orbital_rotations"],
+                                                  constant=float(c["constant"]), z_representation=bool(c["z"]))
+
+    def df_matvec(self, vec, c, norb, nelec):
+        return self.f.linear_operator(self._df(c), norb=norb, nelec=nelec) @ vec
+
+    def qdrift(self, vec, c, norb, nelec):
+        return self.f.simulate_qdrift_double_factorized(
+            vec, self._df(c), float(c["time"]), norb=norb, nelec=nelec, n_steps=int(c["n_steps"]),
+            symmetric=bool(c["symmetric"]), probabilities=bytes(c["probabilities"].astype(np.uint8)).decode(),
+            n_samples=int(c["n_samples"]), seed=int(c["seed"]))
+
 
 def run_case(api, c):
     kind = str(c["kind"])
@@ -154,6 +196,8 @@ def run_case(api, c):
         got = api.dc_matvec(vec, c, norb, nelec)
     elif kind == "dc_split_op":
         got = api.dc_split_op(vec, c, norb, nelec)
+    elif kind in ("ucj_unbalanced", "ucj_spinless", "df_matvec", "qdrift"):
+        got = getattr(api, kind)(vec, c, norb, nelec)
     else:
         raise AssertionError(kind)
     assert np.array_equal(vec, before), "the input vector was modified (copy=True semantics)"
@@ -167,8 +211,9 @@ def test_fixture_is_complete():
     kinds = {str(c["kind"]) for c in CASES.values()}
     assert kinds >= {"orbital_rotation", "orbital_rotation_spinless", "diag_coulomb", "diag_coulomb_spinless",
                      "num_op_sum", "contract_diag_coulomb", "contract_num_op_sum", "ucj", "trotter_df",
-                     "dc_matvec", "dc_split_op", "zero_one", "one", "random_unitary"}
-    assert len(STATE_CASES) >= 80
+                     "dc_matvec", "dc_split_op", "zero_one", "one", "random_unitary",
+                     "ucj_unbalanced", "ucj_spinless", "df_matvec", "qdrift"}
+    assert len(STATE_CASES) >= 93
 
 
 # ----------------------------------------------------------------------------- CPU: pin the oracle
