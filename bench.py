@@ -142,7 +142,8 @@ def ncu_traffic(kernel: str):
     import csv
     import glob
 
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*c2*_ncu_metrics.csv")), key=os.path.getmtime)
+    # newest = last by name (r1_..., r1s4_..., r2_...): file times do not survive the copy to the GPU box
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*c2*_ncu_metrics.csv")))
     if not files:
         return None, None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
