@@ -24,6 +24,12 @@ namespace ffb {
 void read_phase_cycles(unsigned long long *out, int reset);
 }
 #endif
+#ifdef FFB_DEBUG_TIMELINE
+namespace ffb {
+void read_timeline(void *out, int *counts);
+int timeline_capacity();
+}
+#endif
 
 static_assert(ffb::kMaxLow == ffb::kMaxLowDev, "kMaxLow mismatch");
 
@@ -818,6 +824,13 @@ int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const do
 int ffb_debug_phase_cycles(unsigned long long *out, int reset) {
   ffb::read_phase_cycles(out, reset);
   return FFB_OK;
+}
+#endif
+
+#ifdef FFB_DEBUG_TIMELINE
+int ffb_debug_timeline(void *out, int *counts) {
+  ffb::read_timeline(out, counts);
+  return ffb::timeline_capacity();
 }
 #endif
 

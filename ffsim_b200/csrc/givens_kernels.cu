@@ -27,7 +27,7 @@ __device__ int g_debug_knobs = 0;
 #define FFB_KNOB(bit) 0
 #endif
 
-#ifdef FFB_DEBUG_TIMING
+#if defined(FFB_DEBUG_TIMING)
 // per-phase cycle counters (developer builds only): lane 0 of every warp accumulates clock64()
 // deltas in a private shared-memory row; rows are flushed to global memory when the CTA ends
 __device__ unsigned long long g_phase_cycles[16];
@@ -39,9 +39,39 @@ __shared__ unsigned long long s_phase_cycles[32][8];
     if ((threadIdx.x & 31) == 0) s_phase_cycles[threadIdx.x >> 5][k] += (unsigned long long)(_t1 - _t0); \
     _t0 = clock64();                                                                 \
   } while (0)
+#define FFB_TRESTART() _t0 = clock64()
+#elif defined(FFB_DEBUG_TIMELINE)
+// per-warp timeline (developer builds only): for the first tile of CTA 0, lane 0 of every warp logs
+// (phase, begin, end) of everything it does; scripts/timeline.py turns the log into per-scheduler
+// occupancy of the FP64 and LSU phases.  Phases as in scripts/phase_timing.py.
+constexpr int kTlEvents = 2048;
+struct TlEvent {
+  unsigned long long t0, t1;
+  int phase, pad;
+};
+__device__ TlEvent g_tl[32][kTlEvents];
+__device__ int g_tl_count[32];
+__shared__ int s_tl_on;
+#define FFB_T0() long long _t0 = clock64()
+#define FFB_TACC(k)                                                      \
+  do {                                                                   \
+    long long _t1 = clock64();                                           \
+    if (s_tl_on && (threadIdx.x & 31) == 0) {                            \
+      const int _w = threadIdx.x >> 5, _i = g_tl_count[_w];              \
+      if (_i < kTlEvents) {                                              \
+        g_tl[_w][_i].t0 = (unsigned long long)_t0;                       \
+        g_tl[_w][_i].t1 = (unsigned long long)_t1;                       \
+        g_tl[_w][_i].phase = (k);                                        \
+        g_tl_count[_w] = _i + 1;                                         \
+      }                                                                  \
+    }                                                                    \
+    _t0 = clock64();                                                     \
+  } while (0)
+#define FFB_TRESTART() _t0 = clock64()
 #else
 #define FFB_T0()
 #define FFB_TACC(k)
+#define FFB_TRESTART()
 #endif
 
 // ---------------------------------------------------------------- constexpr combinatorics
@@ -303,6 +333,10 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
   if (tid < 32 * 8) s_phase_cycles[tid >> 3][tid & 7] = 0;
   __syncthreads();
 #endif
+#ifdef FFB_DEBUG_TIMELINE
+  if (tid == 0) s_tl_on = blockIdx.x == 0;
+  __syncthreads();
+#endif
   int cached_group = -1;
 
   for (long long unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
@@ -431,9 +465,7 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
             const unsigned o_row = offtab_sa + (cur.entry >> 24) * (unsigned)(kOffRowDev * sizeof(uint32_t));
             process_dispatch<W>(cur.mp, a_addr, o_row, p, run0, run1);
           }
-#ifdef FFB_DEBUG_TIMING
-          _t0 = clock64();
-#endif
+          FFB_TRESTART();
           cur = nxt;
           g = g_next;
         }
@@ -506,6 +538,9 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
     FFB_TACC(7);
     __syncthreads();
     FFB_TACC(6);
+#ifdef FFB_DEBUG_TIMELINE
+    if (tid == 0) s_tl_on = 0;  // only the CTA's first tile is logged
+#endif
   }
 #ifdef FFB_DEBUG_TIMING
   __syncthreads();
@@ -555,6 +590,17 @@ int fused_pass_ctas_per_sm(int w, int threads, size_t smem) {
 
 #ifdef FFB_DEBUG_KNOBS
 void set_debug_knobs(int v) { cudaMemcpyToSymbol(g_debug_knobs, &v, sizeof(int)); }
+#endif
+#ifdef FFB_DEBUG_TIMELINE
+// out: 32 x kTlEvents records of (t0, t1, phase); counts: 32 ints; the log is cleared afterwards
+void read_timeline(void *out, int *counts) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_tl, sizeof(g_tl));
+  cudaMemcpyFromSymbol(counts, g_tl_count, sizeof(g_tl_count));
+  int z[32] = {0};
+  cudaMemcpyToSymbol(g_tl_count, z, sizeof(z));
+}
+int timeline_capacity() { return kTlEvents; }
 #endif
 #ifdef FFB_DEBUG_TIMING
 void read_phase_cycles(unsigned long long *out, int reset) {
