@@ -16,7 +16,7 @@ import math
 import numpy as np
 
 from ffsim_b200.hamiltonians import DiagonalCoulombHamiltonian, DoubleFactorizedHamiltonian
-from ffsim_b200.variational import UCJOpSpinBalanced
+from ffsim_b200.variational import UCJOpSpinBalanced, UCJOpSpinless, UCJOpSpinUnbalanced
 
 
 def random_state_vector(dim: int, *, seed=None, dtype=complex) -> np.ndarray:
@@ -113,6 +113,93 @@ def random_ucj_op_spin_balanced(
                 mask[cols, rows] = True
             diag_coulomb_mats[:, which] *= mask
     return UCJOpSpinBalanced(
+        diag_coulomb_mats=diag_coulomb_mats,
+        orbital_rotations=orbital_rotations,
+        final_orbital_rotation=final_orbital_rotation,
+    )
+
+
+def _pair_mask(norb: int, pairs, symmetric: bool) -> np.ndarray:
+    """Boolean mask of the matrix entries an interaction-pair list allows."""
+    mask = np.zeros((norb, norb), dtype=bool)
+    if pairs:
+        rows, cols = zip(*pairs)
+        mask[rows, cols] = True
+        if symmetric:
+            mask[cols, rows] = True
+    return mask
+
+
+def random_ucj_op_spin_unbalanced(
+    norb: int,
+    *,
+    n_reps: int = 1,
+    interaction_pairs=None,
+    with_final_orbital_rotation: bool = False,
+    diag_coulomb_mean: float = 0.0,
+    diag_coulomb_scale: float = 2 * math.pi,
+    diag_coulomb_normal: bool = False,
+    seed=None,
+) -> UCJOpSpinUnbalanced:
+    """python/ffsim/random/random.py:668-790: same draws in the same order (per repetition J_aa, J_ab,
+    J_bb; then per repetition the alpha and beta rotations; then the final pair)."""
+    pairs_aa, pairs_ab, pairs_bb = (None, None, None) if interaction_pairs is None else interaction_pairs
+    rng = np.random.default_rng(seed)
+    same_spin = _random_symmetric_matrix_normal if diag_coulomb_normal else _random_symmetric_matrix_uniform
+
+    def cross():
+        if diag_coulomb_normal:
+            return rng.normal(loc=diag_coulomb_mean, scale=diag_coulomb_scale, size=(norb, norb))
+        return diag_coulomb_mean + rng.uniform(-0.5 * diag_coulomb_scale, 0.5 * diag_coulomb_scale, size=(norb, norb))
+
+    reps = []
+    for _ in range(n_reps):
+        mat_aa = same_spin(norb, mean=diag_coulomb_mean, scale=diag_coulomb_scale, seed=rng)
+        mat_ab = cross()
+        mat_bb = same_spin(norb, mean=diag_coulomb_mean, scale=diag_coulomb_scale, seed=rng)
+        reps.append(np.stack([mat_aa, mat_ab, mat_bb]))
+    diag_coulomb_mats = np.stack(reps)
+    rots = []
+    for _ in range(n_reps):
+        rot_a = random_unitary(norb, seed=rng)
+        rots.append(np.stack([rot_a, random_unitary(norb, seed=rng)]))
+    orbital_rotations = np.stack(rots)
+    final_orbital_rotation = None
+    if with_final_orbital_rotation:
+        final_a = random_unitary(norb, seed=rng)
+        final_orbital_rotation = np.stack([final_a, random_unitary(norb, seed=rng)])
+    for which, pairs, symmetric in ((0, pairs_aa, True), (1, pairs_ab, False), (2, pairs_bb, True)):
+        if pairs is not None:
+            diag_coulomb_mats[:, which] *= _pair_mask(norb, pairs, symmetric)
+    return UCJOpSpinUnbalanced(
+        diag_coulomb_mats=diag_coulomb_mats,
+        orbital_rotations=orbital_rotations,
+        final_orbital_rotation=final_orbital_rotation,
+    )
+
+
+def random_ucj_op_spinless(
+    norb: int,
+    *,
+    n_reps: int = 1,
+    interaction_pairs=None,
+    with_final_orbital_rotation: bool = False,
+    diag_coulomb_mean: float = 0.0,
+    diag_coulomb_scale: float = 2 * math.pi,
+    diag_coulomb_normal: bool = False,
+    seed=None,
+) -> UCJOpSpinless:
+    """python/ffsim/random/random.py:803-880."""
+    rng = np.random.default_rng(seed)
+    draw = _random_symmetric_matrix_normal if diag_coulomb_normal else _random_symmetric_matrix_uniform
+    diag_coulomb_mats = np.stack(
+        [draw(norb, mean=diag_coulomb_mean, scale=diag_coulomb_scale, seed=rng) for _ in range(n_reps)]
+    )
+    orbital_rotations = np.stack([random_unitary(norb, seed=rng) for _ in range(n_reps)])
+    final_orbital_rotation = random_unitary(norb, seed=rng) if with_final_orbital_rotation else None
+    if interaction_pairs is not None:
+        diag_coulomb_mats *= _pair_mask(norb, interaction_pairs, True)
+    return UCJOpSpinless(
         diag_coulomb_mats=diag_coulomb_mats,
         orbital_rotations=orbital_rotations,
         final_orbital_rotation=final_orbital_rotation,

@@ -263,6 +263,19 @@ def main():
                                                        symmetric=symmetric, probabilities=probs,
                                                        n_samples=n_samples, seed=seed))
 
+    # generators of the widened operators, explicit seeds (pins ffsim_b200/random.py)
+    for fn_name, norb, kw in [
+        ("random_ucj_op_spin_unbalanced", 5, dict(n_reps=2, with_final_orbital_rotation=True, seed=5101)),
+        ("random_ucj_op_spin_unbalanced", 4, dict(n_reps=1, diag_coulomb_normal=True, diag_coulomb_mean=0.3, seed=5102)),
+        ("random_ucj_op_spinless", 5, dict(n_reps=2, with_final_orbital_rotation=True, seed=5103)),
+        ("random_ucj_op_spinless", 4, dict(n_reps=3, diag_coulomb_normal=True, seed=5104)),
+    ]:
+        op = getattr(rr, fn_name)(norb, **kw)
+        add(f"random_op/{fn_name}_{kw['seed']}", kind=fn_name, n=norb, seed=kw["seed"], n_reps=kw["n_reps"],
+            final=int(kw.get("with_final_orbital_rotation", False)), normal=int(kw.get("diag_coulomb_normal", False)),
+            mean=kw.get("diag_coulomb_mean", 0.0), diag_coulomb_mats=op.diag_coulomb_mats,
+            orbital_rotations=op.orbital_rotations, final_orbital_rotation=opt(op.final_orbital_rotation))
+
     flat = {}
     for name, arrays in CASES.items():
         for k, v in arrays.items():

@@ -204,7 +204,7 @@ def run_case(api, c):
     return got
 
 
-STATE_CASES = [n for n in CASES if not n.startswith(("random/", "tables/"))]
+STATE_CASES = [n for n in CASES if not n.startswith(("random/", "random_op/", "tables/"))]
 
 
 def test_fixture_is_complete():
@@ -235,6 +235,24 @@ def test_generators_bit_exact(name):
     for mod in (rand, prod):
         got = getattr(mod, kind)(n, seed=seed)
         assert np.array_equal(got, c["expected"]), f"{mod.__name__}.{kind}"
+
+
+@pytest.mark.parametrize("name", names("random_op/"))
+def test_operator_generators_bit_exact(name):
+    """ffsim_b200/random.py against python/ffsim/random/random.py:668-880 (UCJ spin-unbalanced, spinless)."""
+    import ffsim_b200.random as prod
+
+    c = CASES[name]
+    op = getattr(prod, str(c["kind"]))(int(c["n"]), n_reps=int(c["n_reps"]),
+                                       with_final_orbital_rotation=bool(c["final"]),
+                                       diag_coulomb_normal=bool(c["normal"]), diag_coulomb_mean=float(c["mean"]),
+                                       seed=int(c["seed"]))
+    assert np.array_equal(op.diag_coulomb_mats, c["diag_coulomb_mats"])
+    assert np.array_equal(op.orbital_rotations, c["orbital_rotations"])
+    want_final = opt(c["final_orbital_rotation"])
+    assert (op.final_orbital_rotation is None) == (want_final is None)
+    if want_final is not None:
+        assert np.array_equal(op.final_orbital_rotation, want_final)
 
 
 @pytest.mark.parametrize("name", names("tables/"))
