@@ -154,3 +154,42 @@ extern "C" int ffb_hostcheck_dump_schedule(int norb, int nocc, const int *q, int
   }
   return 0;
 }
+
+// Shared-memory bank behaviour of the register-block gathers, from the block lists the kernel will
+// consume: lanes of a quarter-warp (8 consecutive items of a class; the block index runs fastest)
+// access rows base + o[t]; rows that agree modulo 8 fall in the same 16-byte bank group.  Counts the
+// quarter-warps of every (pass, group, sub-pass, class) and the extra wavefronts their first access
+// needs (0 when the eight rows differ modulo 8).  out[0] = quarter-warps, out[1] = extra wavefronts.
+extern "C" int ffb_hostcheck_gather_conflicts(int norb, int nocc, const int *q, int n, int64_t *out) {
+  PlanOptions opt = current_options();
+  std::vector<int> qq(q, q + n);
+  SideSchedule sched = build_schedule(norb, nocc, qq, opt);
+  int64_t quarters = 0, extra = 0;
+  for (const PassSchedule &ps : sched.passes) {
+    PassTablesHost T = build_pass_tables(norb, nocc, ps);
+    for (const PassGroupHost &G : T.groups) {
+      for (size_t s = 0; s < ps.subs.size(); ++s) {
+        const GroupSubHost &gs = G.subs[s];
+        const uint16_t *offtab = T.off.data() + s * kMaxLow * kOffRow;
+        for (int sg = 0; sg < gs.n_seg; ++sg) {
+          const int mp = gs.seg_mp[sg];
+          const int coff = class_offset(ps.subs[s].w, mp);
+          for (int b0 = 0; b0 < gs.seg_count[sg]; b0 += 8) {
+            int hits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int lanes = std::min(8, gs.seg_count[sg] - b0), worst = 0;
+            for (int l = 0; l < lanes; ++l) {
+              uint32_t e = gs.blocks[gs.seg_begin[sg] + b0 + l];
+              int row = (int)(e & 0xFFFFFF) + offtab[(e >> 24) * kOffRow + coff];
+              worst = std::max(worst, ++hits[row & 7]);
+            }
+            ++quarters;
+            extra += worst - 1;
+          }
+        }
+      }
+    }
+  }
+  out[0] = quarters;
+  out[1] = extra;
+  return 0;
+}

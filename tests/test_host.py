@@ -284,3 +284,22 @@ def test_qdrift_probabilities_match_oracle(z_rep, rank_one):
         ffsim.qdrift_probabilities(ham, "optimal")
     with pytest.raises(ValueError, match="Unsupported"):
         ffsim.qdrift_probabilities(ham, "nonsense")
+
+
+@pytest.mark.parametrize("norb, k, bound", [(16, 5, 0.36), (18, 7, 0.67), (20, 8, 0.52), (24, 6, 0.55)])
+def test_block_lists_are_ordered_for_conflict_free_gathers(norb, k, bound):
+    """plan.cpp orders the blocks of a class so that, within one l' group, eight consecutive blocks
+    start in different bank groups.  What is left are the group tails (the residues of a group are not
+    evenly populated); the bounds are the values of round 1 (+0.05) and guard against regressions of the
+    ordering -- the natural (H', r) order gives 0.72, 0.90, 0.73, 0.72 extra wavefronts per quarter-warp."""
+    hc = _hostcheck()
+    hc.ffb_hostcheck_gather_conflicts.restype = ctypes.c_int
+    hc.ffb_hostcheck_gather_conflicts.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                                  ctypes.POINTER(ctypes.c_int64)]
+    rots, _ = givens_decomposition(rand.random_unitary(norb, seed=3))
+    q = (ctypes.c_int * len(rots))(*[min(int(r[2]), int(r[3])) for r in rots])
+    out = (ctypes.c_int64 * 2)()
+    assert hc.ffb_hostcheck_gather_conflicts(norb, k, q, len(rots), out) == 0
+    quarters, extra = out[0], out[1]
+    assert quarters > 100
+    assert extra <= bound * quarters, f"{extra} extra wavefronts in {quarters} quarter-warps"
