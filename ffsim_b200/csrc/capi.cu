@@ -120,10 +120,7 @@ struct DevicePass {
   GroupSubDev *d_gsub = nullptr;
   uint32_t *d_off = nullptr;
   int blk_cap = 4;  // longest block list of any (group, sub-pass), rounded up to 4 entries
-  struct GroupOffsets {
-    uint32_t tabrow_off, combo_base_off, combo_low_off, gsub_off;
-  };
-  std::vector<GroupOffsets> goff;
+  std::vector<DevicePassTables::GroupOffsets> goff;
   ~DevicePass() {
     cudaFree(d_u32);
     cudaFree(d_u8);
@@ -144,63 +141,15 @@ int build_device_pass(int norb, int nocc, const PassSchedule &ps, std::unique_pt
   std::unique_ptr<DevicePass> dp(new DevicePass());
   dp->sched = ps;
   dp->host = build_pass_tables(norb, nocc, ps);
-  std::vector<uint32_t> u32;
-  std::vector<uint8_t> u8;
-  std::vector<GroupSubDev> gsub;
-  const int n_sub = (int)ps.subs.size();
-  auto pad4 = [&]() {  // block lists are staged into shared memory with 16-byte copies
-    while (u32.size() % 4) u32.push_back(0);
-  };
-  for (PassGroupHost &G : dp->host.groups) {
-    DevicePass::GroupOffsets go;
-    go.tabrow_off = (uint32_t)u32.size();
-    u32.insert(u32.end(), G.tabrow.begin(), G.tabrow.end());
-    go.combo_base_off = (uint32_t)u32.size();
-    u32.insert(u32.end(), G.combo_base.begin(), G.combo_base.end());
-    go.combo_low_off = (uint32_t)u8.size();
-    u8.insert(u8.end(), G.combo_low.begin(), G.combo_low.end());
-    go.gsub_off = (uint32_t)gsub.size();
-    for (int s = 0; s < n_sub; ++s) {
-      GroupSubHost &gs = G.subs[s];
-      GroupSubDev d;
-      std::memset(&d, 0, sizeof(d));
-      pad4();
-      d.blocks_off = (uint32_t)u32.size();
-      d.n_seg = gs.n_seg;
-      d.n_blocks = (int)gs.blocks.size();
-      dp->blk_cap = std::max(dp->blk_cap, (d.n_blocks + 3) & ~3);
-      for (int k = 0; k < gs.n_seg && k < kMaxSeg; ++k) {
-        d.seg[k].mp = gs.seg_mp[k];
-        d.seg[k].begin = gs.seg_begin[k];
-        d.seg[k].count = gs.seg_count[k];
-        d.seg[k].inv_count = 0xFFFFFFFFu / (unsigned)std::max(1, gs.seg_count[k]) + 1u;
-      }
-      u32.insert(u32.end(), gs.blocks.begin(), gs.blocks.end());
-      pad4();
-      gsub.push_back(d);
-      std::vector<uint32_t>().swap(gs.blocks);
-    }
-    dp->goff.push_back(go);
-    std::vector<uint32_t>().swap(G.tabrow);
-  }
-  if (u32.size() >= (1ull << 32)) return fail(FFB_EINTERNAL, "pass tables exceed 32-bit offsets");
+  DevicePassTables D = pack_device_tables(ps, dp->host);  // (plan.cpp; the host emulator reads the same)
+  dp->goff = D.goff;
+  dp->blk_cap = D.blk_cap;
+  if (D.u32.size() >= (1ull << 32)) return fail(FFB_EINTERNAL, "pass tables exceed 32-bit offsets");
   int rc;
-  if ((rc = upload(u32, &dp->d_u32)) != FFB_OK) return rc;
-  if ((rc = upload(u8, &dp->d_u8)) != FFB_OK) return rc;
-  if ((rc = upload(gsub, &dp->d_gsub)) != FFB_OK) return rc;
-  // device form of the block-offset tables: byte offsets, every class starting on a 16-byte boundary
-  std::vector<uint32_t> off32((size_t)n_sub * kMaxLowDev * kOffRowDev, 0);
-  for (int s = 0; s < n_sub; ++s) {
-    const int w = ps.subs[s].w;
-    for (int lp = 0; lp < kMaxLow; ++lp)
-      for (int mp = 1; mp < w; ++mp) {
-        const int n = (int)binom(w, mp);
-        for (int t = 0; t < n; ++t)
-          off32[((size_t)s * kMaxLowDev + lp) * kOffRowDev + dev_class_offset(w, mp) + t] =
-              16u * dp->host.off[((size_t)s * kMaxLow + lp) * kOffRow + class_offset(w, mp) + t];
-      }
-  }
-  if ((rc = upload(off32, &dp->d_off)) != FFB_OK) return rc;
+  if ((rc = upload(D.u32, &dp->d_u32)) != FFB_OK) return rc;
+  if ((rc = upload(D.u8, &dp->d_u8)) != FFB_OK) return rc;
+  if ((rc = upload(D.gsub, &dp->d_gsub)) != FFB_OK) return rc;
+  if ((rc = upload(D.off32, &dp->d_off)) != FFB_OK) return rc;
   *out = std::move(dp);
   return FFB_OK;
 }

@@ -103,6 +103,23 @@ struct PassTablesHost {
 };
 PassTablesHost build_pass_tables(int norb, int nocc, const PassSchedule &pass);
 
+// The same tables in the form fused_pass_kernel reads: one u32 pool (tile row tables, combination
+// bases, 16-byte aligned register-block lists), the u8 pool (combination -> row table), the segment
+// descriptors of every (group, sub-pass) and the block-offset tables as byte offsets with every class
+// on a 16-byte boundary.  Consumes the block lists and row tables of `T` (they are large).
+struct DevicePassTables {
+  struct GroupOffsets {
+    uint32_t tabrow_off, combo_base_off, combo_low_off, gsub_off;
+  };
+  std::vector<uint32_t> u32;
+  std::vector<uint8_t> u8;
+  std::vector<GroupSubDev> gsub;
+  std::vector<uint32_t> off32;  // [n_sub][kMaxLowDev][kOffRowDev]
+  std::vector<GroupOffsets> goff;  // one per group of `T`
+  int blk_cap = 4;  // longest block list of any (group, sub-pass), rounded up to 4 entries
+};
+DevicePassTables pack_device_tables(const PassSchedule &pass, PassTablesHost &T);
+
 // Dispatch units of a sub-pass: maximal runs (length <= kMaxRunLen) of consecutive rotations
 // whose pair positions descend by one.  rq[] holds positions relative to the pass window;
 // q_hi_rel is relative to the sub-window start q0.

@@ -344,6 +344,60 @@ PassTablesHost build_pass_tables(int norb, int nocc, const PassSchedule &pass) {
   return T;
 }
 
+DevicePassTables pack_device_tables(const PassSchedule &ps, PassTablesHost &T) {
+  DevicePassTables D;
+  std::vector<uint32_t> &u32 = D.u32;
+  const int n_sub = (int)ps.subs.size();
+  auto pad4 = [&]() {  // block lists are staged into shared memory with 16-byte copies
+    while (u32.size() % 4) u32.push_back(0);
+  };
+  for (PassGroupHost &G : T.groups) {
+    DevicePassTables::GroupOffsets go;
+    go.tabrow_off = (uint32_t)u32.size();
+    u32.insert(u32.end(), G.tabrow.begin(), G.tabrow.end());
+    go.combo_base_off = (uint32_t)u32.size();
+    u32.insert(u32.end(), G.combo_base.begin(), G.combo_base.end());
+    go.combo_low_off = (uint32_t)D.u8.size();
+    D.u8.insert(D.u8.end(), G.combo_low.begin(), G.combo_low.end());
+    go.gsub_off = (uint32_t)D.gsub.size();
+    for (int s = 0; s < n_sub; ++s) {
+      GroupSubHost &gs = G.subs[s];
+      GroupSubDev d;
+      std::memset(&d, 0, sizeof(d));
+      pad4();
+      d.blocks_off = (uint32_t)u32.size();
+      d.n_seg = gs.n_seg;
+      d.n_blocks = (int)gs.blocks.size();
+      D.blk_cap = std::max(D.blk_cap, (d.n_blocks + 3) & ~3);
+      for (int k = 0; k < gs.n_seg && k < kMaxSeg; ++k) {
+        d.seg[k].mp = gs.seg_mp[k];
+        d.seg[k].begin = gs.seg_begin[k];
+        d.seg[k].count = gs.seg_count[k];
+        d.seg[k].inv_count = 0xFFFFFFFFu / (unsigned)std::max(1, gs.seg_count[k]) + 1u;
+      }
+      u32.insert(u32.end(), gs.blocks.begin(), gs.blocks.end());
+      pad4();
+      D.gsub.push_back(d);
+      std::vector<uint32_t>().swap(gs.blocks);
+    }
+    D.goff.push_back(go);
+    std::vector<uint32_t>().swap(G.tabrow);
+  }
+  // block-offset tables: byte offsets, every class starting on a 16-byte boundary
+  D.off32.assign((size_t)n_sub * kMaxLowDev * kOffRowDev, 0);
+  for (int s = 0; s < n_sub; ++s) {
+    const int w = ps.subs[s].w;
+    for (int lp = 0; lp < kMaxLow; ++lp)
+      for (int mp = 1; mp < w; ++mp) {
+        const int n = (int)binom(w, mp);
+        for (int t = 0; t < n; ++t)
+          D.off32[((size_t)s * kMaxLowDev + lp) * kOffRowDev + dev_class_offset(w, mp) + t] =
+              16u * T.off[((size_t)s * kMaxLow + lp) * kOffRow + class_offset(w, mp) + t];
+      }
+  }
+  return D;
+}
+
 }  // namespace ffb
 
 using namespace ffb;

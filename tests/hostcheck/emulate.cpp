@@ -193,3 +193,137 @@ extern "C" int ffb_hostcheck_gather_conflicts(int norb, int nocc, const int *q, 
   out[1] = extra;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Device view.  The same rotation, but walking exactly the data the kernel walks, the way it walks it:
+// the packed tables of pack_device_tables() (u32/u8 pools, GroupSubDev segment descriptors with their
+// reciprocal counts, byte-offset tables with 16-byte aligned classes, 16-byte aligned block lists), the
+// column-major tile with the bank-aware column stride, the chunk-prefix rows, the boustrophedon dealing
+// of 32-item chunks to `nwarp` warps, and fetch_chunk's arithmetic including the multiply-high division.
+// Mirrors fused_pass_kernel / fetch_chunk / process_item of csrc/givens_kernels.cu line by line; any
+// change there must be made here too (that is the point: it pins the index logic without a GPU).
+static inline uint32_t umulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline int fast_div_host(int n, uint32_t inv) { return inv ? (int)umulhi32((uint32_t)n, inv) : n; }
+
+extern "C" int ffb_hostcheck_apply_side_device(int norb, int nocc, const ffb_givens_rotation *rots, int n_rot,
+                                               void *vec /* dim x n_cols, row-major */, int64_t n_cols,
+                                               int64_t smem_bytes, int min_cols, int sub_window, int cols_req,
+                                               int nwarp) {
+  PlanOptions opt = current_options();
+  if (smem_bytes > 0) opt.smem_bytes = smem_bytes;
+  if (min_cols > 0) opt.min_cols = min_cols;
+  if (sub_window > 0) opt.sub_window = sub_window;
+  cplx *data = reinterpret_cast<cplx *>(vec);
+  std::vector<NormRot> nr;
+  std::vector<int> q;
+  for (int k = 0; k < n_rot; ++k) {
+    nr.push_back(normalise(rots[k]));
+    q.push_back(nr.back().q);
+  }
+  if (nocc == 0 || nocc == norb) q.clear();
+  SideSchedule sched = build_schedule(norb, nocc, q, opt);
+  constexpr int kChunkRow = 8;
+  for (const PassSchedule &ps : sched.passes) {
+    PassTablesHost T = build_pass_tables(norb, nocc, ps);
+    std::vector<int> group_R, group_has;
+    std::vector<size_t> group_combos;
+    for (const PassGroupHost &G : T.groups) {
+      group_R.push_back(G.R);
+      group_has.push_back(G.has_blocks ? 1 : 0);
+      group_combos.push_back(G.combo_base.size());
+    }
+    DevicePassTables D = pack_device_tables(ps, T);
+    const int n_sub = (int)ps.subs.size();
+    for (size_t gi = 0; gi < group_R.size(); ++gi) {
+      if (!group_has[gi]) continue;
+      const int R = group_R[gi];
+      const int cols = (int)std::max<int64_t>(1, std::min<int64_t>(cols_req, n_cols));
+      const int Rp = tile_col_stride(R, cols);
+      if (Rp < R || (Rp - R) > 7) return -201;
+      const DevicePassTables::GroupOffsets &go = D.goff[gi];
+      const int64_t n_strips = (n_cols + cols - 1) / cols;
+      // chunk-prefix rows (the kernel builds them when it caches a group)
+      std::vector<uint16_t> cend((size_t)n_sub * kChunkRow);
+      for (int sp = 0; sp < n_sub; ++sp) {
+        const GroupSubDev &g = D.gsub[go.gsub_off + sp];
+        int acc = 0;
+        for (int k = 0; k < kChunkRow - 1; ++k) {
+          if (k < g.n_seg && k < kMaxSeg) acc += (g.seg[k].count * cols + 31) >> 5;
+          cend[(size_t)sp * kChunkRow + k] = (k < g.n_seg && k < kMaxSeg) ? (uint16_t)acc : (uint16_t)0xFFFF;
+        }
+        cend[(size_t)sp * kChunkRow + kChunkRow - 1] = (uint16_t)acc;
+      }
+      for (size_t combo = 0; combo < group_combos[gi]; ++combo) {
+        const uint32_t rowbase = D.u32[go.combo_base_off + combo];
+        const uint32_t *tab = D.u32.data() + go.tabrow_off + (size_t)D.u8[go.combo_low_off + combo] * R;
+        for (int64_t strip = 0; strip < n_strips; ++strip) {
+          const int64_t col0 = strip * cols;
+          const int ncv = (int)std::min<int64_t>(cols, n_cols - col0);
+          std::vector<cplx> tile((size_t)Rp * cols, cplx(0, 0));
+          for (int r = 0; r < R; ++r)
+            for (int j = 0; j < ncv; ++j) tile[(size_t)j * Rp + r] = data[((int64_t)rowbase + tab[r]) * n_cols + col0 + j];
+          for (int s = 0; s < n_sub; ++s) {
+            const SubPass &sp = ps.subs[s];
+            const GroupSubDev &gs = D.gsub[go.gsub_off + s];
+            if (gs.blocks_off % 4 || gs.n_blocks > D.blk_cap) return -202;
+            const uint32_t *blk = D.u32.data() + gs.blocks_off;  // (staged copy of n_blocks entries)
+            const uint32_t *offtab = D.off32.data() + (size_t)s * kMaxLowDev * kOffRowDev;
+            const uint16_t *ce = cend.data() + (size_t)s * kChunkRow;
+            const int n_chunks = ce[kChunkRow - 1];
+            std::vector<char> used(tile.size(), 0);
+            int items_done = 0;
+            for (int warp = 0; warp < nwarp; ++warp) {
+              for (int k = 0;; ++k) {
+                const int g = k * nwarp + ((k & 1) ? nwarp - 1 - warp : warp);
+                if (g >= n_chunks) break;
+                // fetch_chunk
+                const int c0 = ce[0], c1 = ce[1], c2 = ce[2], c3 = ce[3];
+                int sg = 0, base = 0;
+                if (g >= c0) sg = 1, base = c0;
+                if (g >= c1) sg = 2, base = c1;
+                if (g >= c2) sg = 3, base = c2;
+                if (g >= c3) sg = 4, base = c3;
+                const SegDev &sq = gs.seg[sg];
+                const int mp = sq.mp & 0xFF, count = sq.count;
+                std::vector<uint64_t> pats = strings_of(sp.w, mp);
+                for (int lane = 0; lane < 32; ++lane) {
+                  const int item = ((g - base) << 5) + lane;
+                  if (item >= count * cols) continue;
+                  const int col = fast_div_host(item, sq.inv_count);
+                  const int b = item - col * count;
+                  if (col < 0 || col >= cols || b < 0 || b >= count || sq.begin + b >= gs.n_blocks) return -203;
+                  const uint32_t entry = blk[sq.begin + b];
+                  // process_item: byte addresses relative to the tile
+                  const uint32_t a_addr = (uint32_t)(col * Rp + (int)(entry & 0xFFFFFFu)) << 4;
+                  const uint32_t *o = offtab + (entry >> 24) * kOffRowDev + dev_class_offset(sp.w, mp);
+                  std::vector<size_t> idx(pats.size());
+                  for (size_t t = 0; t < pats.size(); ++t) {
+                    const uint32_t byte = a_addr + o[t];
+                    if (byte % 16) return -204;
+                    idx[t] = byte / 16;
+                    if (idx[t] >= tile.size() || idx[t] < (size_t)col * Rp || idx[t] >= (size_t)col * Rp + R) return -205;
+                    if (used[idx[t]]) return -206;  // blocks of a sub-pass are disjoint
+                    used[idx[t]] = 1;
+                  }
+                  for (int rr = sp.rot_begin; rr < sp.rot_end; ++rr) {
+                    const NormRot &gr = nr[ps.rot_index[rr]];
+                    const int qq = gr.q - ps.lo - sp.q0;
+                    for (size_t t = 0; t < pats.size(); ++t) {
+                      const uint64_t S = pats[t];
+                      if (((S >> qq) & 3) == 1) zrot(tile[idx[rank_of(S)]], tile[idx[rank_of(S ^ (3ull << qq))]], gr.c, gr.s);
+                    }
+                  }
+                  ++items_done;
+                }
+              }
+            }
+            if (items_done != gs.n_blocks * cols) return -207;  // every (block, column) exactly once
+          }
+          for (int r = 0; r < R; ++r)
+            for (int j = 0; j < ncv; ++j) data[((int64_t)rowbase + tab[r]) * n_cols + col0 + j] = tile[(size_t)j * Rp + r];
+        }
+      }
+    }
+  }
+  return 0;
+}

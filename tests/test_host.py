@@ -303,3 +303,49 @@ def test_block_lists_are_ordered_for_conflict_free_gathers(norb, k, bound):
     quarters, extra = out[0], out[1]
     assert quarters > 100
     assert extra <= bound * quarters, f"{extra} extra wavefronts in {quarters} quarter-warps"
+
+
+# ---------------------------------------------------------------- the kernel's index path, from the packed device tables
+def _emulate_device_view(norb, k, n_cols, smem, min_cols, sub_window, cols, nwarp, seed):
+    from ffsim_b200.linalg.givens import _decompose_raw
+
+    hc = _hostcheck()
+    hc.ffb_hostcheck_apply_side_device.restype = ctypes.c_int
+    hc.ffb_hostcheck_apply_side_device.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    rng = np.random.default_rng(seed)
+    dim = math.comb(norb, k)
+    u = rand.random_unitary(norb, seed=rng)
+    vec = rand.random_state_vector(dim * n_cols, seed=rng).reshape(dim, n_cols)
+    rots, _ = _decompose_raw(u)
+    rots = np.ascontiguousarray(rots)
+    got = np.ascontiguousarray(vec.copy())
+    rc = hc.ffb_hostcheck_apply_side_device(norb, k, L.ptr(rots), len(rots), L.ptr(got), n_cols, smem, min_cols,
+                                            sub_window, cols, nwarp)
+    assert rc == 0, f"device-view invariant {rc} failed for norb={norb} k={k}"
+    want = vec.copy()
+    rotations, _ = givens.givens_decomposition(u)
+    gates._rotate_one_spin(want, (rotations, []), norb, k)  # the phases are a separate kernel stage
+    return np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-300)
+
+
+@pytest.mark.parametrize("norb,k,n_cols,smem,min_cols,sub_window,cols,nwarp", [
+    (6, 3, 5, 220 * 1024, 3, 6, 3, 16),      # one window, ragged last column strip
+    (8, 4, 7, 220 * 1024, 3, 6, 8, 16),      # eight tile columns (stride rule for cols = 8)
+    (8, 3, 4, 4096, 2, 4, 2, 4),             # several passes and tile groups, 4-orbital blocks, 4 warps
+    (9, 4, 3, 8192, 1, 5, 1, 16),            # single-column tiles
+    (10, 5, 6, 220 * 1024, 3, 6, 3, 16),
+    (10, 2, 9, 2048, 4, 3, 4, 8),
+    (12, 6, 2, 220 * 1024, 3, 6, 2, 16),     # BASELINE C1 sector
+    (14, 5, 3, 32 * 1024, 3, 6, 3, 16),
+    (16, 5, 1, 220 * 1024, 3, 6, 1, 16),     # BASELINE C2 sector, one column
+    (7, 7, 2, 220 * 1024, 3, 6, 2, 16),      # full shell: nothing to rotate
+    (5, 1, 3, 220 * 1024, 3, 6, 3, 12),
+])
+def test_device_view_of_the_plan_tables(norb, k, n_cols, smem, min_cols, sub_window, cols, nwarp):
+    """tests/hostcheck/emulate.cpp::ffb_hostcheck_apply_side_device walks the packed device tables the way
+    fused_pass_kernel does (chunk dealing, multiply-high division, byte offsets, column-major tile) and must
+    reproduce the oracle's rotation."""
+    err = _emulate_device_view(norb, k, n_cols, smem, min_cols, sub_window, cols, nwarp, seed=100 * norb + k)
+    assert err < 1e-13
