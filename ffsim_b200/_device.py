@@ -53,11 +53,18 @@ def is_sharded(vec: Any) -> bool:
     return isinstance(vec, ShardedVector)
 
 
-def local_block(t, dim_a: int):
-    """(tensor holding the locally stored alpha rows, first row, number of rows)."""
+def local_block(t, dim_a: int, dim_b: int):
+    """The locally stored block of the (dim_a x dim_b) state:
+    (tensor, first alpha row, rows, first beta column, columns, row stride)."""
     if is_sharded(t):
-        return t.local, t.row0, t.n_rows
-    return t, 0, dim_a
+        return t.block()
+    return t, 0, dim_a, 0, dim_b, dim_b
+
+
+def same_layout(t, out) -> None:
+    """Binary operators on sharded vectors need both operands in the same distribution."""
+    if is_sharded(t) and is_sharded(out):
+        out.set_layout_like(t)
 
 
 def empty_like(t):

@@ -91,8 +91,13 @@ EXPORTS = {
     "ffb_apply_num_op_sum_evolution": (c_int, _P, _P, _P, _P, _P, c_int64, c_int64, _P),
     "ffb_contract_diag_coulomb": (c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int64, c_int64, _P),
     "ffb_contract_num_op_sum": (c_int, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int64, _P),
+    "ffb_apply_diag_coulomb_evolution_block": (c_int, _P, _P, _P, _P, _P, c_int, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P),
+    "ffb_apply_num_op_sum_evolution_block": (c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P),
+    "ffb_contract_diag_coulomb_block": (c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, _P),
+    "ffb_contract_num_op_sum_block": (c_int, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, _P),
     "ffb_transpose": (c_int, _P, _P, c_int64, c_int64, c_int64, c_int64, _P),
     "ffb_exchange_blocks": (c_int, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P),
+    "ffb_copy_blocks": (c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P),
     "ffb_vdot": (c_int, _P, _P, c_int64, _P, _P),
     "ffb_axpby": (c_int, C128, _P, C128, _P, c_int64, _P),
     "ffb_profile_begin": (c_int,),

@@ -28,8 +28,20 @@ class Tables:
 
 
 @lru_cache(maxsize=None)
-def get_tables(norb: int, nocc: int) -> Tables:
+def _tables_for_device(norb: int, nocc: int, device: int) -> Tables:
     return Tables(norb, nocc)
+
+
+def get_tables(norb: int, nocc: int) -> Tables:
+    """The (norb, nocc) sector's handle for the CURRENT CUDA device.
+
+    A handle owns device buffers (the uploaded strings, per-call scratch), so one handle per
+    device: the same sector used on cuda:0 and then on cuda:1 must not share them.
+    """
+    import torch
+
+    device = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    return _tables_for_device(int(norb), int(nocc), device)
 
 
 @lru_cache(maxsize=None)

@@ -41,15 +41,16 @@ def _get_mats(mat: Any, norb: int, z_representation: bool):
 def _contract_device(t, out, mats, norb, nelec, z_representation, accumulate) -> None:
     aa, ab, bb = mats
     ta, tb = get_tables(norb, nelec[0]), get_tables(norb, nelec[1])
-    data, row0, n_rows = _device.local_block(t, ta.dim)
-    out_data, _, _ = _device.local_block(out, ta.dim)
+    _device.same_layout(t, out)
+    data, row0, n_rows, col0, n_cols, ld = _device.local_block(t, ta.dim, tb.dim)
+    out_data = _device.local_block(out, ta.dim, tb.dim)[0]
     with torch.cuda.device(data.device):
         _device.sync_device()
         _lib.check(
-            _lib.lib.ffb_contract_diag_coulomb(
+            _lib.lib.ffb_contract_diag_coulomb_block(
                 ta.handle, tb.handle, _lib.ptr(aa), _lib.ptr(ab), _lib.ptr(bb),
                 int(bool(z_representation)), data.data_ptr(), out_data.data_ptr(), int(bool(accumulate)),
-                row0, n_rows, _device.stream_ptr(),
+                row0, n_rows, col0, n_cols, ld, _device.stream_ptr(),
             )
         )
 

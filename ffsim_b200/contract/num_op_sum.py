@@ -15,14 +15,15 @@ from ffsim_b200.gates.orbital_rotation import _check_dim, _rotate_device
 
 def _contract_device(t, out, coeffs: np.ndarray, norb, nelec, accumulate) -> None:
     ta, tb = get_tables(norb, nelec[0]), get_tables(norb, nelec[1])
-    data, row0, n_rows = _device.local_block(t, ta.dim)
-    out_data, _, _ = _device.local_block(out, ta.dim)
+    _device.same_layout(t, out)
+    data, row0, n_rows, col0, n_cols, ld = _device.local_block(t, ta.dim, tb.dim)
+    out_data = _device.local_block(out, ta.dim, tb.dim)[0]
     with torch.cuda.device(data.device):
         _device.sync_device()
         _lib.check(
-            _lib.lib.ffb_contract_num_op_sum(
+            _lib.lib.ffb_contract_num_op_sum_block(
                 ta.handle, tb.handle, _lib.ptr(coeffs), _lib.ptr(coeffs), data.data_ptr(), out_data.data_ptr(),
-                int(bool(accumulate)), row0, n_rows, _device.stream_ptr(),
+                int(bool(accumulate)), row0, n_rows, col0, n_cols, ld, _device.stream_ptr(),
             )
         )
 

@@ -44,8 +44,9 @@ namespace {
 
 // ---- optional launch profiling (bench.py): CUDA events around the hot kernels,
 // recorded on the stream they are launched on.
-enum { kProfFused = 0, kProfDiag = 1, kProfTranspose = 2, kProfOther = 3, kProfKinds = 4 };
-const char *const kProfNames[kProfKinds] = {"fused_pass_kernel", "diag_kernel", "transpose_kernel", "other"};
+enum { kProfFused = 0, kProfDiag = 1, kProfTranspose = 2, kProfOther = 3, kProfExchange = 4, kProfKinds = 5 };
+const char *const kProfNames[kProfKinds] = {"fused_pass_kernel", "diag_kernel", "transpose_kernel", "other",
+                                             "exchange_kernel"};
 struct ProfState {
   bool enabled = false;
   std::mutex mu;
@@ -55,7 +56,7 @@ struct ProfState {
     double bytes;
   };
   std::vector<Rec> recs;
-  long long launches[kProfKinds] = {0, 0, 0, 0};
+  long long launches[kProfKinds] = {0, 0, 0, 0, 0};
 };
 ProfState g_prof;
 
@@ -651,12 +652,19 @@ enum { kSlotFactor = 0, kSlotMat = 1, kSlotMatAB = 2, kSlotPartial = 3 };
 // shared body of the four diagonal entry points
 int diag_op(bool contract, ffb_tables *ta, ffb_tables *tb, const void *m_aa, const void *m_ab,
             const void *m_bb, int zrep, const void *vec, void *out, int accumulate, int64_t row0,
-            int64_t n_rows, cudaStream_t st) {
+            int64_t n_rows, int64_t col0, int64_t n_cols, int64_t ld, cudaStream_t st) {
   if (!ta || !tb) return fail(FFB_EINVAL, "diagonal operator: NULL tables");
   if (ta->norb != tb->norb) return fail(FFB_EINVAL, "diagonal operator: norb mismatch");
   if (row0 < 0 || n_rows < 0 || row0 + n_rows > ta->dim)
     return fail(FFB_EINVAL, "diagonal operator: row block outside the alpha sector");
-  if (n_rows == 0 || tb->dim == 0) return FFB_OK;
+  if (n_cols < 0) {  // the whole beta sector, contiguous rows
+    col0 = 0;
+    n_cols = tb->dim;
+    ld = tb->dim;
+  }
+  if (col0 < 0 || col0 + n_cols > tb->dim || ld < n_cols)
+    return fail(FFB_EINVAL, "diagonal operator: column block outside the beta sector");
+  if (n_rows == 0 || n_cols == 0) return FFB_OK;
   if (!vec || !out) return fail(FFB_EINVAL, "diagonal operator: NULL state");
   int rc;
   if ((rc = ensure_device_strings(ta)) != FFB_OK) return rc;
@@ -691,10 +699,10 @@ int diag_op(bool contract, ffb_tables *ta, ffb_tables *tb, const void *m_aa, con
     FFB_CUDA(cudaMemcpyAsync(d_ab, m_ab, (size_t)norb * norb * elem, cudaMemcpyHostToDevice, st));
   }
   {
-    const double amps = (double)n_rows * (double)tb->dim;
+    const double amps = (double)n_rows * (double)n_cols;
     ProfScope prof(kProfDiag, (contract && accumulate ? 48.0 : 32.0) * amps, st);
     FFB_CUDA(launch_diag(contract, ta->d_strings, tb->d_strings, fa, fb, d_ab, vec, out, row0, n_rows,
-                         tb->dim, norb, zrep, accumulate, di.sm_count, st));
+                         col0, n_cols, ld, norb, zrep, accumulate, di.sm_count, st));
   }
   return FFB_OK;
 }
@@ -703,17 +711,34 @@ int diag_op(bool contract, ffb_tables *ta, ffb_tables *tb, const void *m_aa, con
 
 extern "C" {
 
+int ffb_apply_diag_coulomb_evolution_block(ffb_tables *tables_a, ffb_tables *tables_b,
+                                           const ffb_c128 *mat_exp_aa, const ffb_c128 *mat_exp_ab,
+                                           const ffb_c128 *mat_exp_bb, int z_representation,
+                                           void *vec_dev, int64_t row0, int64_t n_rows, int64_t col0,
+                                           int64_t n_cols, int64_t ld, void *stream) {
+  return diag_op(false, tables_a, tables_b, mat_exp_aa, mat_exp_ab, mat_exp_bb, z_representation,
+                 vec_dev, vec_dev, 0, row0, n_rows, col0, n_cols, ld, (cudaStream_t)stream);
+}
+
 int ffb_apply_diag_coulomb_evolution(ffb_tables *tables_a, ffb_tables *tables_b,
                                      const ffb_c128 *mat_exp_aa, const ffb_c128 *mat_exp_ab,
                                      const ffb_c128 *mat_exp_bb, int z_representation,
                                      void *vec_dev, int64_t row0, int64_t n_rows, void *stream) {
-  return diag_op(false, tables_a, tables_b, mat_exp_aa, mat_exp_ab, mat_exp_bb, z_representation,
-                 vec_dev, vec_dev, 0, row0, n_rows, (cudaStream_t)stream);
+  return ffb_apply_diag_coulomb_evolution_block(tables_a, tables_b, mat_exp_aa, mat_exp_ab, mat_exp_bb,
+                                                z_representation, vec_dev, row0, n_rows, 0, -1, 0, stream);
 }
 
 int ffb_apply_num_op_sum_evolution(ffb_tables *tables_a, ffb_tables *tables_b,
                                    const ffb_c128 *phases_a, const ffb_c128 *phases_b,
                                    void *vec_dev, int64_t row0, int64_t n_rows, void *stream) {
+  return ffb_apply_num_op_sum_evolution_block(tables_a, tables_b, phases_a, phases_b, vec_dev, row0, n_rows,
+                                              0, -1, 0, stream);
+}
+
+int ffb_apply_num_op_sum_evolution_block(ffb_tables *tables_a, ffb_tables *tables_b,
+                                         const ffb_c128 *phases_a, const ffb_c128 *phases_b,
+                                         void *vec_dev, int64_t row0, int64_t n_rows, int64_t col0,
+                                         int64_t n_cols, int64_t ld, void *stream) {
   if (!tables_a || !tables_b) return fail(FFB_EINVAL, "ffb_apply_num_op_sum_evolution: NULL tables");
   // prod_{i in occ} p_i == the same-spin factor of diag(p): M[j][k] = (j == k ? p_j : 1)
   const int norb = tables_a->norb;
@@ -726,7 +751,7 @@ int ffb_apply_num_op_sum_evolution(ffb_tables *tables_a, ffb_tables *tables_b,
   if (phases_b) diag(phases_b, mb);
   if (!phases_a && !phases_b) return FFB_OK;
   return diag_op(false, tables_a, tables_b, phases_a ? ma.data() : nullptr, nullptr,
-                 phases_b ? mb.data() : nullptr, 0, vec_dev, vec_dev, 0, row0, n_rows,
+                 phases_b ? mb.data() : nullptr, 0, vec_dev, vec_dev, 0, row0, n_rows, col0, n_cols, ld,
                  (cudaStream_t)stream);
 }
 
@@ -734,6 +759,15 @@ int ffb_contract_diag_coulomb(ffb_tables *tables_a, ffb_tables *tables_b, const 
                               const double *mat_ab, const double *mat_bb, int z_representation,
                               const void *vec_dev, void *out_dev, int accumulate, int64_t row0,
                               int64_t n_rows, void *stream) {
+  return ffb_contract_diag_coulomb_block(tables_a, tables_b, mat_aa, mat_ab, mat_bb, z_representation, vec_dev,
+                                         out_dev, accumulate, row0, n_rows, 0, -1, 0, stream);
+}
+
+int ffb_contract_diag_coulomb_block(ffb_tables *tables_a, ffb_tables *tables_b, const double *mat_aa,
+                                    const double *mat_ab, const double *mat_bb, int z_representation,
+                                    const void *vec_dev, void *out_dev, int accumulate, int64_t row0,
+                                    int64_t n_rows, int64_t col0, int64_t n_cols, int64_t ld,
+                                    void *stream) {
   if (!tables_a) return fail(FFB_EINVAL, "ffb_contract_diag_coulomb: NULL tables");
   const int norb = tables_a->norb;
   std::vector<double> sa, sab, sb;
@@ -749,12 +783,20 @@ int ffb_contract_diag_coulomb(ffb_tables *tables_a, ffb_tables *tables_b, const 
     mat_bb = scaled(mat_bb, sb);
   }
   return diag_op(true, tables_a, tables_b, mat_aa, mat_ab, mat_bb, z_representation, vec_dev,
-                 out_dev, accumulate, row0, n_rows, (cudaStream_t)stream);
+                 out_dev, accumulate, row0, n_rows, col0, n_cols, ld, (cudaStream_t)stream);
 }
 
 int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const double *coeffs_a,
                             const double *coeffs_b, const void *vec_dev, void *out_dev,
                             int accumulate, int64_t row0, int64_t n_rows, void *stream) {
+  return ffb_contract_num_op_sum_block(tables_a, tables_b, coeffs_a, coeffs_b, vec_dev, out_dev, accumulate,
+                                       row0, n_rows, 0, -1, 0, stream);
+}
+
+int ffb_contract_num_op_sum_block(ffb_tables *tables_a, ffb_tables *tables_b, const double *coeffs_a,
+                                  const double *coeffs_b, const void *vec_dev, void *out_dev,
+                                  int accumulate, int64_t row0, int64_t n_rows, int64_t col0,
+                                  int64_t n_cols, int64_t ld, void *stream) {
   if (!tables_a || !tables_b) return fail(FFB_EINVAL, "ffb_contract_num_op_sum: NULL tables");
   const int norb = tables_a->norb;
   std::vector<double> ma, mb;
@@ -765,7 +807,7 @@ int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const do
   if (coeffs_a) diag(coeffs_a, ma);
   if (coeffs_b) diag(coeffs_b, mb);
   return diag_op(true, tables_a, tables_b, coeffs_a ? ma.data() : nullptr, nullptr,
-                 coeffs_b ? mb.data() : nullptr, 0, vec_dev, out_dev, accumulate, row0, n_rows,
+                 coeffs_b ? mb.data() : nullptr, 0, vec_dev, out_dev, accumulate, row0, n_rows, col0, n_cols, ld,
                  (cudaStream_t)stream);
 }
 
@@ -807,8 +849,8 @@ int ffb_profile_end(char *buf, size_t buflen) {
   FFB_CUDA(cudaDeviceSynchronize());
   std::lock_guard<std::mutex> lk(g_prof.mu);
   g_prof.enabled = false;
-  double ms[kProfKinds] = {0, 0, 0, 0}, bytes[kProfKinds] = {0, 0, 0, 0};
-  long long timed[kProfKinds] = {0, 0, 0, 0};
+  double ms[kProfKinds] = {0, 0, 0, 0, 0}, bytes[kProfKinds] = {0, 0, 0, 0, 0};
+  long long timed[kProfKinds] = {0, 0, 0, 0, 0};
   for (auto &r : g_prof.recs) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
@@ -845,24 +887,25 @@ int ffb_transpose(const void *in_dev, void *out_dev, int64_t n_rows, int64_t n_c
   return FFB_OK;
 }
 
-int ffb_exchange_blocks(const void *src_dev, int64_t src_ld, int n_dst, const int64_t *rows,
-                        const int64_t *width, const int64_t *src_off, void *const *dst_dev,
-                        const int64_t *dst_off, const int64_t *dst_ld, void *stream) {
-  if (n_dst == 0) return FFB_OK;
-  if (n_dst < 0 || n_dst > kMaxExchangeDst || !rows || !width || !src_off || !dst_dev || !dst_off || !dst_ld)
-    return fail(FFB_EINVAL, "ffb_exchange_blocks: bad argument");
+int ffb_copy_blocks(const void *src_dev, int n_blocks, const int64_t *rows, const int64_t *width,
+                    const int64_t *src_off, const int64_t *src_ld, void *const *dst_dev,
+                    const int64_t *dst_off, const int64_t *dst_ld, void *stream) {
+  if (n_blocks == 0) return FFB_OK;
+  if (n_blocks < 0 || n_blocks > kMaxExchangeDst || !rows || !width || !src_off || !src_ld || !dst_dev ||
+      !dst_off || !dst_ld)
+    return fail(FFB_EINVAL, "ffb_copy_blocks: bad argument");
   ExchangeParams p;
   std::memset(&p, 0, sizeof(p));
   p.src = src_dev;
-  p.src_ld = src_ld;
-  p.n_dst = n_dst;
-  for (int d = 0; d < n_dst; ++d) {
-    if (rows[d] < 0 || width[d] < 0) return fail(FFB_EINVAL, "ffb_exchange_blocks: negative block size");
+  p.n_dst = n_blocks;
+  for (int d = 0; d < n_blocks; ++d) {
+    if (rows[d] < 0 || width[d] < 0) return fail(FFB_EINVAL, "ffb_copy_blocks: negative block size");
     if (rows[d] > 0 && width[d] > 0 && (!src_dev || !dst_dev[d]))
-      return fail(FFB_EINVAL, "ffb_exchange_blocks: NULL buffer");
+      return fail(FFB_EINVAL, "ffb_copy_blocks: NULL buffer");
     p.rows[d] = width[d] > 0 ? rows[d] : 0;
     p.width[d] = width[d];
     p.src_off[d] = src_off[d];
+    p.src_ld[d] = src_ld[d];
     p.dst[d] = dst_dev[d];
     p.dst_off[d] = dst_off[d];
     p.dst_ld[d] = dst_ld[d];
@@ -871,9 +914,20 @@ int ffb_exchange_blocks(const void *src_dev, int64_t src_ld, int n_dst, const in
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc != FFB_OK) return rc;
-  ProfScope prof(kProfOther, 0.0, (cudaStream_t)stream);
+  double bytes = 0.0;
+  for (int d = 0; d < n_blocks; ++d) bytes += 32.0 * (double)p.rows[d] * (double)p.width[d];
+  ProfScope prof(kProfExchange, bytes, (cudaStream_t)stream);
   FFB_CUDA(launch_exchange(p, di.sm_count, (cudaStream_t)stream));
   return FFB_OK;
+}
+
+int ffb_exchange_blocks(const void *src_dev, int64_t src_ld, int n_dst, const int64_t *rows,
+                        const int64_t *width, const int64_t *src_off, void *const *dst_dev,
+                        const int64_t *dst_off, const int64_t *dst_ld, void *stream) {
+  if (n_dst < 0 || n_dst > kMaxExchangeDst) return fail(FFB_EINVAL, "ffb_exchange_blocks: bad argument");
+  int64_t lds[kMaxExchangeDst];
+  for (int d = 0; d < n_dst; ++d) lds[d] = src_ld;
+  return ffb_copy_blocks(src_dev, n_dst, rows, width, src_off, lds, dst_dev, dst_off, dst_ld, stream);
 }
 
 int ffb_vdot(const void *x_dev, const void *y_dev, int64_t n, void *result_dev, void *stream) {

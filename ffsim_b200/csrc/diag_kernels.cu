@@ -77,7 +77,8 @@ struct DiagParams {
   const void *mab;     // [norb*norb] or NULL
   const double2 *vec;
   double2 *out;
-  long long row0, n_rows, dim_b;
+  long long row0, n_rows;     // alpha rows [row0, row0 + n_rows) are stored, row k at vec + k * ld
+  long long col0, n_cols, ld; // beta columns [col0, col0 + n_cols) are stored
   int norb, zrep, accumulate;
 };
 
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(128, (kRowsPerWarp * kDiagUnroll >= 8) ? 4 : 6
   const int per_row = 32 + nch * kChunkSize;  // pm[32] then the tables
   T *wbase = reinterpret_cast<T *>(smem_raw) + (size_t)warp * kRowsPerWarp * per_row;
   const T *__restrict__ rowfac = reinterpret_cast<const T *>(p.rowfac);
-  const T *__restrict__ colfac = reinterpret_cast<const T *>(p.colfac);
+  const T *__restrict__ colfac = p.colfac ? reinterpret_cast<const T *>(p.colfac) + p.col0 : nullptr;
+  const uint32_t *__restrict__ strings_b = p.strings_b + p.col0;
   const T *__restrict__ mab = reinterpret_cast<const T *>(p.mab);
   const long long n_groups = (p.n_rows + kRowsPerWarp - 1) / kRowsPerWarp;
   const long long gw = (long long)blockIdx.x * wpb + warp, nw = (long long)gridDim.x * wpb;
@@ -144,31 +146,31 @@ __global__ void __launch_bounds__(128, (kRowsPerWarp * kDiagUnroll >= 8) ? 4 : 6
     }
     __syncwarp();
     const int n_valid = (int)min((long long)kRowsPerWarp, p.n_rows - row_first);
-    const double2 *__restrict__ src = p.vec + row_first * p.dim_b;
-    double2 *__restrict__ dst = p.out + row_first * p.dim_b;
+    const double2 *__restrict__ src = p.vec + row_first * p.ld;
+    double2 *__restrict__ dst = p.out + row_first * p.ld;
     const T *tab0 = wbase + 32;
-    for (long long b0 = lane; b0 < p.dim_b; b0 += 32 * kDiagUnroll) {
+    for (long long b0 = lane; b0 < p.n_cols; b0 += 32 * kDiagUnroll) {
       uint32_t str[kDiagUnroll];
       T cf[kDiagUnroll];
       double2 v[kDiagUnroll][kRowsPerWarp], old[kDiagUnroll][kRowsPerWarp];
 #pragma unroll
       for (int u = 0; u < kDiagUnroll; ++u) {
         const long long b = b0 + 32 * u;
-        if (b < p.dim_b) {
-          str[u] = p.strings_b[b];
+        if (b < p.n_cols) {
+          str[u] = strings_b[b];
           cf[u] = colfac ? colfac[b] : S::one();
 #pragma unroll
           for (int rr = 0; rr < kRowsPerWarp; ++rr)
             if (rr < n_valid) {
-              v[u][rr] = src[rr * p.dim_b + b];
-              if (CONTRACT && p.accumulate) old[u][rr] = dst[rr * p.dim_b + b];
+              v[u][rr] = src[rr * p.ld + b];
+              if (CONTRACT && p.accumulate) old[u][rr] = dst[rr * p.ld + b];
             }
         }
       }
 #pragma unroll
       for (int u = 0; u < kDiagUnroll; ++u) {
         const long long b = b0 + 32 * u;
-        if (b < p.dim_b) {
+        if (b < p.n_cols) {
 #pragma unroll
           for (int rr = 0; rr < kRowsPerWarp; ++rr)
             if (rr < n_valid) {
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(128, (kRowsPerWarp * kDiagUnroll >= 8) ? 4 : 6
               } else {
                 o = make_double2(v[u][rr].x * f.x - v[u][rr].y * f.y, v[u][rr].x * f.y + v[u][rr].y * f.x);
               }
-              dst[rr * p.dim_b + b] = o;
+              dst[rr * p.ld + b] = o;
             }
         }
       }
@@ -300,9 +302,10 @@ cudaError_t launch_side_factor(bool contract, const uint32_t *strings, long long
 
 cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t *strings_b,
                         const void *rowfac, const void *colfac, const void *mab, const void *vec,
-                        void *out, long long row0, long long n_rows, long long dim_b, int norb,
-                        int zrep, int accumulate, int sm_count, cudaStream_t stream) {
-  if (n_rows <= 0 || dim_b <= 0) return cudaSuccess;
+                        void *out, long long row0, long long n_rows, long long col0, long long n_cols,
+                        long long ld, int norb, int zrep, int accumulate, int sm_count,
+                        cudaStream_t stream) {
+  if (n_rows <= 0 || n_cols <= 0) return cudaSuccess;
   DiagParams p;
   p.strings_a = strings_a;
   p.strings_b = strings_b;
@@ -313,7 +316,9 @@ cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t
   p.out = (double2 *)out;
   p.row0 = row0;
   p.n_rows = n_rows;
-  p.dim_b = dim_b;
+  p.col0 = col0;
+  p.n_cols = n_cols;
+  p.ld = ld;
   p.norb = norb;
   p.zrep = zrep;
   p.accumulate = accumulate;

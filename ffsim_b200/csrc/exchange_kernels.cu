@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(kExThreads) exchange_kernel(const __grid_const
     const int d = (int)(unit % p.n_dst);  // consecutive CTAs feed different links
     const long long row = unit / p.n_dst;
     if (row >= p.rows[d]) continue;
-    const double2 *__restrict__ src = reinterpret_cast<const double2 *>(p.src) + p.src_off[d] + row * p.src_ld;
+    const double2 *__restrict__ src = reinterpret_cast<const double2 *>(p.src) + p.src_off[d] + row * p.src_ld[d];
     double2 *__restrict__ dst = reinterpret_cast<double2 *>(p.dst[d]) + p.dst_off[d] + row * p.dst_ld[d];
     const long long width = p.width[d];
     for (long long c0 = threadIdx.x; c0 < width; c0 += (long long)kExThreads * kExUnroll) {

@@ -36,15 +36,14 @@ cudaError_t launch_transpose(const void *in, void *out, long long n_rows, long l
 
 namespace ffb {
 // One rank's side of the distributed transpose: block d is rows[d] x width[d] elements, read from
-// src + src_off[d] (row stride src_ld) and written to dst[d] + dst_off[d] (row stride dst_ld[d]).
+// src + src_off[d] (row stride src_ld[d]) and written to dst[d] + dst_off[d] (row stride dst_ld[d]).
 constexpr int kMaxExchangeDst = 16;
 struct ExchangeParams {
   const void *src;
-  long long src_ld;
   int n_dst;
   long long max_rows;
   void *dst[kMaxExchangeDst];
-  long long src_off[kMaxExchangeDst], dst_off[kMaxExchangeDst], dst_ld[kMaxExchangeDst];
+  long long src_off[kMaxExchangeDst], src_ld[kMaxExchangeDst], dst_off[kMaxExchangeDst], dst_ld[kMaxExchangeDst];
   long long rows[kMaxExchangeDst], width[kMaxExchangeDst];
 };
 cudaError_t launch_exchange(const ExchangeParams &p, int sm_count, cudaStream_t stream);
@@ -54,8 +53,9 @@ cudaError_t launch_side_factor(bool contract, const uint32_t *strings, long long
                                cudaStream_t stream);
 cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t *strings_b,
                         const void *rowfac, const void *colfac, const void *mab, const void *vec,
-                        void *out, long long row0, long long n_rows, long long dim_b, int norb,
-                        int zrep, int accumulate, int sm_count, cudaStream_t stream);
+                        void *out, long long row0, long long n_rows, long long col0, long long n_cols,
+                        long long ld, int norb, int zrep, int accumulate, int sm_count,
+                        cudaStream_t stream);
 cudaError_t launch_vdot(const void *x, const void *y, long long n, void *partial, int n_partial,
                         void *result, int sm_count, cudaStream_t stream);
 cudaError_t launch_axpby(double ar, double ai, const void *x, double br, double bi, void *y,

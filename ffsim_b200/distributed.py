@@ -1,26 +1,33 @@
-"""Row-sharded state vectors: one process per GPU, alpha strings split across ranks.
+"""Sharded state vectors: one process per GPU, one state distributed over all of them.
 
-Layout: rank r holds the contiguous block of alpha rows
-[a_off[r], a_off[r+1]) of the (dim_a x dim_b) state, all beta columns.  Then
+A ``ShardedVector`` holds its share of the (dim_a x dim_b) state in one of two distributions
+(SURVEY.md section 8e):
 
-* beta-side Givens rotations, diagonal Coulomb / number-operator evolutions and
-  contractions are rank-local (the kernels take the row offset of the block);
-* alpha-side rotations couple rows of different ranks: the state is redistributed
-  to column shards [dim_a x (b_off[r+1]-b_off[r])] with one all-to-all over
-  NVLink (NCCL), rotated locally along the row index, and redistributed back;
-* scalars (vdot, norm) are a local reduction plus an all_reduce.
+* ``"rows"``: rank r holds alpha rows [a_off[r], a_off[r+1]) x all beta columns.  Beta-side Givens
+  rotations are local;
+* ``"cols"``: rank r holds all alpha rows x beta columns [b_off[r], b_off[r+1]).  Alpha-side
+  rotations are local.
+
+Diagonal Coulomb / number-operator evolutions and contractions, axpby and dot products are local in
+either distribution (the kernels take the row and column offsets of the block).  The state is NOT
+moved back after an alpha-side rotation: it stays where the last operation left it, and the next
+rotation starts with the spin sector that is local.  An orbital rotation on both spins therefore
+costs ONE redistribution (an all-to-all over NVLink), a LUCJ circuit with L layers L + 1 of them.
+Scalars (vdot, norm) are a local reduction plus an all_reduce.
 
 A ``ShardedVector`` can be passed wherever the public functions take ``vec``
 (``apply_orbital_rotation``, ``apply_diag_coulomb_evolution``, ``apply_unitary``,
-``linear_operator(...) @ vec``, ...).  The reference has no counterpart: it is a
-single-process NumPy code.
+``linear_operator(...) @ vec``, ...).  The reference has no counterpart: it is a single-process
+NumPy code.
 
-Two implementations of the redistribution exist.  On one NVLink/NVSwitch box the shards live
-in symmetric (peer-mapped) memory and ``ffb_exchange_blocks`` stores every block straight into its
-final place in the destination GPU's buffer: one kernel instead of pack + all-to-all + unpack, no
-send/receive staging buffers.  Everywhere else (``gloo`` on CPU tensors -- which is how the host-side
-logic is tested without GPUs --, more than two ranks unless ``FFSIM_B200_EXCHANGE=p2p``, or
-``FFSIM_B200_EXCHANGE=nccl``) it is ``all_to_all_single``.
+Two implementations of the redistribution exist.  On one NVLink/NVSwitch box the shards live in
+symmetric (peer-mapped) memory and ``ffb_exchange_blocks`` stores every block straight into its
+final place in the destination GPU's buffer: one kernel, no staging.  Otherwise it is NCCL
+``all_to_all_single`` with the strided side packed / unpacked by the same library kernel
+(``ffb_exchange_blocks`` with local destinations); on CPU tensors (``gloo``: how the host-side logic is
+tested without GPUs) the pack / unpack are plain tensor copies.  ``FFSIM_B200_EXCHANGE`` = ``p2p`` /
+``nccl`` forces one of them, ``auto`` (default) takes the peer-memory path up to
+``FFSIM_B200_P2P_MAX_WORLD`` ranks (default 2, the validated configuration).
 """
 
 from __future__ import annotations
@@ -29,7 +36,6 @@ import ctypes
 import math
 import os
 import weakref
-from typing import Sequence
 
 import numpy as np
 import torch
@@ -45,10 +51,16 @@ def partition(n: int, world: int) -> list[int]:
     return offs
 
 
-class ShardedVector:
-    """A state vector whose alpha rows are distributed over the ranks of ``group``."""
+ROWS, COLS = "rows", "cols"
 
-    def __init__(self, local: torch.Tensor, norb: int, nelec: tuple[int, int], group=None):
+# counters of the redistribution (bench.py / tests read them): exchanges done and bytes this rank sent
+STATS = {"exchanges": 0, "bytes_sent": 0}
+
+
+class ShardedVector:
+    """A state vector distributed over the ranks of ``group`` (see the module docstring)."""
+
+    def __init__(self, local: torch.Tensor, norb: int, nelec: tuple[int, int], group=None, layout: str = ROWS):
         self.norb = int(norb)
         self.nelec = (int(nelec[0]), int(nelec[1]))
         self.group = group
@@ -60,14 +72,22 @@ class ShardedVector:
         self.b_off = partition(self.dim_b, self.world)
         self.row0 = self.a_off[self.rank]
         self.n_rows = self.a_off[self.rank + 1] - self.row0
+        self.col0 = self.b_off[self.rank]
+        self.n_cols = self.b_off[self.rank + 1] - self.col0
+        if layout not in (ROWS, COLS):
+            raise ValueError(f"layout must be 'rows' or 'cols', got {layout!r}")
+        self.layout = layout
         local = local.reshape(-1)
         if local.dtype != torch.complex128:
             local = local.to(torch.complex128)
-        if local.numel() != self.n_rows * self.dim_b:
-            raise ValueError(
-                f"local block has {local.numel()} entries, expected {self.n_rows} x {self.dim_b}"
-            )
+        if local.numel() != self.local_numel(layout):
+            raise ValueError(f"local block has {local.numel()} entries, expected {self.local_numel(layout)} "
+                             f"for the '{layout}' distribution")
         self.local = local.contiguous()
+        self._symm = None  # the symmetric-memory buffer behind ``local`` (peer-memory path)
+
+    def local_numel(self, layout: str) -> int:
+        return self.n_rows * self.dim_b if layout == ROWS else self.dim_a * self.n_cols
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -103,18 +123,51 @@ class ShardedVector:
     def numel(self) -> int:
         return self.dim_a * self.dim_b
 
+    def block(self):
+        """(tensor, first alpha row, rows, first beta column, columns, row stride) of the local block."""
+        if self.layout == ROWS:
+            return self.local, self.row0, self.n_rows, 0, self.dim_b, self.dim_b
+        return self.local, 0, self.dim_a, self.col0, self.n_cols, self.n_cols
+
     def clone(self) -> "ShardedVector":
-        return ShardedVector(self.local.clone(), self.norb, self.nelec, self.group)
+        return ShardedVector(self.local.clone(), self.norb, self.nelec, self.group, self.layout)
 
     def empty_like(self) -> "ShardedVector":
-        return ShardedVector(torch.empty_like(self.local), self.norb, self.nelec, self.group)
+        return ShardedVector(torch.empty_like(self.local), self.norb, self.nelec, self.group, self.layout)
 
     def copy_(self, other: "ShardedVector") -> "ShardedVector":
+        if other.layout != self.layout:
+            self._adopt(torch.empty(self.local_numel(other.layout), dtype=torch.complex128, device=self.device),
+                        other.layout)
         self.local.copy_(other.local)
         return self
 
+    def _adopt(self, local: torch.Tensor, layout: str, symm=None) -> None:
+        """New storage for the shard.  A symmetric buffer the vector owned goes back to the pool unless it
+        is the one being adopted (``_symm_box`` is what the vector's finalizer releases)."""
+        box = getattr(self, "_symm_box", None)
+        if box is not None and box[0] is not None and box[0] is not symm:
+            _symm_put(box[0], self.local.device if self.local is not None else local.device, self.group)
+            box[0] = None
+        if symm is not None:
+            if box is None:
+                box = self._symm_box = [None]
+                weakref.finalize(self, _symm_release, box, local.device, self.group)
+            box[0] = symm
+        self.local, self.layout, self._symm = local, layout, symm
+
+    def set_layout(self, layout: str) -> "ShardedVector":
+        """Redistribute (collective: every rank calls it) unless already there."""
+        if layout != self.layout:
+            redistribute(self, layout)
+        return self
+
+    def set_layout_like(self, other: "ShardedVector") -> "ShardedVector":
+        return self.set_layout(other.layout)
+
     def gather(self) -> torch.Tensor:
-        """The full vector on every rank (tests / small cases only)."""
+        """The full vector on every rank (tests / small cases only; collective)."""
+        self.set_layout(ROWS)
         if self.world == 1:
             return self.local.clone()
         # all_gather wants equal sizes: pad every block to the largest one
@@ -129,6 +182,7 @@ class ShardedVector:
 
     def vdot(self, other: "ShardedVector") -> complex:
         """<self|other> (conjugate-linear in self), reduced over the ranks."""
+        other.set_layout_like(self)
         if self.local.is_cuda:
             # the library's deterministic two-stage reduction (64-bit length: a C5 shard has 2.3e9
             # amplitudes, more than cuBLAS's 32-bit dot accepts)
@@ -149,84 +203,122 @@ class ShardedVector:
         return math.sqrt(max(self.vdot(self).real, 0.0))
 
 
-# ---------------------------------------------------------------------- redistribution
+# ---------------------------------------------------------------------- strided block copies
 
-def to_column_shards(sv: ShardedVector, release: bool = False) -> torch.Tensor:
-    """All-to-all #1: row shards [n_rows x dim_b] -> column shards [dim_a x n_cols_local].
+def _i64(values):
+    return (ctypes.c_int64 * len(values))(*[int(v) for v in values])
 
-    Each rank sends, to rank d, its rows restricted to d's beta columns; what it receives
-    from rank s are s's rows restricted to its own columns, and concatenating the sources
-    in rank order is exactly the row-major [dim_a x n_cols_local] matrix.
 
-    With ``release`` the row shard's storage is dropped as soon as it has been packed
-    (``sv.local`` becomes None until ``from_column_shards`` rebuilds it), which keeps the
-    peak at two shard-sized buffers.
-    """
+def _copy_blocks(src: torch.Tensor, src_ld, rows, width, src_off, dst_ptrs, dst_off, dst_ld) -> None:
+    """``ffb_copy_blocks``: block d = rows[d] x width[d] elements from ``src + src_off[d]`` (row stride
+    ``src_ld[d]``, or one stride for all blocks) to ``dst_ptrs[d] + dst_off[d]`` (row stride
+    ``dst_ld[d]``).  The destinations are device pointers: local buffers (pack / unpack) or peer memory
+    (the exchange itself)."""
+    from ffsim_b200 import _device, _lib
+
+    n = len(rows)
+    if isinstance(src_ld, int):
+        src_ld = [src_ld] * n
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(p)) for p in dst_ptrs])
+    _lib.check(_lib.lib.ffb_copy_blocks(
+        src.data_ptr(), n, _i64(rows), _i64(width), _i64(src_off), _i64(src_ld), ptrs, _i64(dst_off), _i64(dst_ld),
+        _device.stream_ptr()))
+
+
+def _row_block_geometry(sv: ShardedVector):
+    """Per peer d: the block (my rows x d's columns) inside the rows-distribution shard, and where it
+    sits in d's cols-distribution shard."""
     w, r = sv.world, sv.rank
-    nb_local = sv.b_off[r + 1] - sv.b_off[r]
-    local2d = sv.local.view(sv.n_rows, sv.dim_b)
-    if w == 1:
-        return local2d if release else local2d.clone()
-    send = torch.empty(sv.n_rows * sv.dim_b, dtype=torch.complex128, device=sv.device)
-    in_splits, pos = [], 0
-    for d in range(w):
-        nb = sv.b_off[d + 1] - sv.b_off[d]
-        n = sv.n_rows * nb
-        send[pos : pos + n].view(sv.n_rows, nb).copy_(local2d[:, sv.b_off[d] : sv.b_off[d + 1]])
-        in_splits.append(n)
-        pos += n
-    device = sv.device
-    if release:
-        del local2d
-        sv.local = None
-    out_splits = [(sv.a_off[s + 1] - sv.a_off[s]) * nb_local for s in range(w)]
-    recv = torch.empty(sv.dim_a * nb_local, dtype=torch.complex128, device=device)
-    dist.all_to_all_single(
-        torch.view_as_real(recv), torch.view_as_real(send),
-        output_split_sizes=out_splits, input_split_sizes=in_splits, group=sv.group,
-    )
-    return recv.view(sv.dim_a, nb_local)
+    cols_of = [sv.b_off[d + 1] - sv.b_off[d] for d in range(w)]
+    return {
+        "rows": [sv.n_rows] * w, "width": cols_of,
+        "row_off": [sv.b_off[d] for d in range(w)],                 # offset inside my [n_rows x dim_b] shard
+        "col_off": [sv.a_off[r] * cols_of[d] for d in range(w)],    # offset inside d's [dim_a x cols_of[d]] shard
+        "col_ld": cols_of,
+    }
 
 
-def from_column_shards(sv: ShardedVector, cols: torch.Tensor) -> None:
-    """All-to-all #2: column shards back into ``sv.local`` (row shards).
-
-    When ``sv.local`` was released, ``cols`` is consumed: pass the only reference to it.
-    """
+def _col_block_geometry(sv: ShardedVector):
+    """Per peer d: the block (d's rows x my columns) inside the cols-distribution shard, and where it
+    sits in d's rows-distribution shard."""
     w, r = sv.world, sv.rank
-    nb_local = sv.b_off[r + 1] - sv.b_off[r]
-    device = cols.device
-    if w == 1:
-        if sv.local is None:
-            sv.local = cols.reshape(-1)
-        elif sv.local.data_ptr() != cols.data_ptr():
-            sv.local.view(sv.n_rows, sv.dim_b).copy_(cols)
-        return
-    send = cols.reshape(-1)  # rows of destination d are contiguous
-    in_splits = [(sv.a_off[d + 1] - sv.a_off[d]) * nb_local for d in range(w)]
-    out_splits = [sv.n_rows * (sv.b_off[s + 1] - sv.b_off[s]) for s in range(w)]
-    recv = torch.empty(sv.n_rows * sv.dim_b, dtype=torch.complex128, device=device)
-    dist.all_to_all_single(
-        torch.view_as_real(recv), torch.view_as_real(send),
-        output_split_sizes=out_splits, input_split_sizes=in_splits, group=sv.group,
-    )
-    del send
-    if sv.local is None:
-        cols.untyped_storage().resize_(0)  # hand the column shard's memory back before unpacking
-        sv.local = torch.empty(sv.n_rows * sv.dim_b, dtype=torch.complex128, device=device)
-    local2d = sv.local.view(sv.n_rows, sv.dim_b)
-    pos = 0
-    for s in range(w):
-        nb = sv.b_off[s + 1] - sv.b_off[s]
-        n = sv.n_rows * nb
-        local2d[:, sv.b_off[s] : sv.b_off[s + 1]].copy_(recv[pos : pos + n].view(sv.n_rows, nb))
-        pos += n
+    rows_of = [sv.a_off[d + 1] - sv.a_off[d] for d in range(w)]
+    return {
+        "rows": rows_of, "width": [sv.n_cols] * w,
+        "col_off": [sv.a_off[d] * sv.n_cols for d in range(w)],    # offset inside my [dim_a x n_cols] shard
+        "row_off": [sv.b_off[r]] * w,                                # offset inside d's [rows_of[d] x dim_b] shard
+        "row_ld": [sv.dim_b] * w,
+    }
 
+
+# ---------------------------------------------------------------------- redistribution (all-to-all)
 
 def all_to_all_bytes(sv: ShardedVector) -> int:
     """Bytes this rank sends over NVLink in one redistribution (its off-rank share of the shard)."""
-    own = sv.b_off[sv.rank + 1] - sv.b_off[sv.rank]
-    return 16 * sv.n_rows * (sv.dim_b - own)
+    if sv.layout == ROWS:
+        return 16 * sv.n_rows * (sv.dim_b - sv.n_cols)
+    return 16 * (sv.dim_a - sv.n_rows) * sv.n_cols
+
+
+def _rows_to_cols_a2a(sv: ShardedVector) -> None:
+    """rows -> cols through ``all_to_all_single``.  The send side is strided (a column slice of every
+    local row per destination) and is packed first; what arrives from rank s are s's rows restricted to
+    my columns, and the sources in rank order ARE the row-major [dim_a x n_cols] shard: no unpack."""
+    w = sv.world
+    g = _row_block_geometry(sv)
+    device = sv.device
+    send = torch.empty(sv.n_rows * sv.dim_b, dtype=torch.complex128, device=device)
+    in_splits = [sv.n_rows * g["width"][d] for d in range(w)]
+    pos = [0]
+    for n in in_splits:
+        pos.append(pos[-1] + n)
+    if send.is_cuda:
+        with torch.cuda.device(device):
+            _copy_blocks(sv.local, sv.dim_b, g["rows"], g["width"], g["row_off"], [send.data_ptr()] * w,
+                         pos[:-1], g["width"])
+    else:
+        local2d = sv.local.view(sv.n_rows, sv.dim_b)
+        for d in range(w):
+            send[pos[d] : pos[d + 1]].view(sv.n_rows, g["width"][d]).copy_(
+                local2d[:, sv.b_off[d] : sv.b_off[d + 1]])
+    sv.local = None  # the row shard's storage is dropped before the column shard is allocated
+    out_splits = [(sv.a_off[s + 1] - sv.a_off[s]) * sv.n_cols for s in range(w)]
+    recv = torch.empty(sv.dim_a * sv.n_cols, dtype=torch.complex128, device=device)
+    dist.all_to_all_single(
+        torch.view_as_real(recv), torch.view_as_real(send),
+        output_split_sizes=out_splits, input_split_sizes=in_splits, group=sv.group,
+    )
+    sv._adopt(recv, COLS)
+
+
+def _cols_to_rows_a2a(sv: ShardedVector) -> None:
+    """cols -> rows: the send side is contiguous per destination (d's rows of my column shard); the
+    receive side is unpacked into the [n_rows x dim_b] shard."""
+    w = sv.world
+    g = _col_block_geometry(sv)
+    device = sv.device
+    in_splits = [g["rows"][d] * sv.n_cols for d in range(w)]
+    out_width = [sv.b_off[s + 1] - sv.b_off[s] for s in range(w)]
+    out_splits = [sv.n_rows * out_width[s] for s in range(w)]
+    recv = torch.empty(sv.n_rows * sv.dim_b, dtype=torch.complex128, device=device)
+    dist.all_to_all_single(
+        torch.view_as_real(recv), torch.view_as_real(sv.local),
+        output_split_sizes=out_splits, input_split_sizes=in_splits, group=sv.group,
+    )
+    sv.local = None
+    local = torch.empty(sv.n_rows * sv.dim_b, dtype=torch.complex128, device=device)
+    pos = [0]
+    for n in out_splits:
+        pos.append(pos[-1] + n)
+    if recv.is_cuda:
+        with torch.cuda.device(device):
+            _copy_blocks(recv, out_width, [sv.n_rows] * w, out_width, pos[:-1], [local.data_ptr()] * w,
+                         [sv.b_off[s] for s in range(w)], [sv.dim_b] * w)
+    else:
+        local2d = local.view(sv.n_rows, sv.dim_b)
+        for s in range(w):
+            local2d[:, sv.b_off[s] : sv.b_off[s + 1]].copy_(recv[pos[s] : pos[s + 1]].view(sv.n_rows, out_width[s]))
+    sv._adopt(local, ROWS)
 
 
 # ---------------------------------------------------------------------- peer-memory exchange
@@ -263,17 +355,21 @@ def _symm_put(buf: _SymmBuffer, device, group) -> None:
     _SYMM_POOL.setdefault((id(group), str(device), buf.numel), []).append(buf)
 
 
+def _symm_release(box, device, group) -> None:
+    """Finalizer of a vector that lives in symmetric memory: its current buffer goes back to the pool."""
+    if box[0] is not None:
+        _symm_put(box[0], device, group)
+        box[0] = None
+
+
 def p2p_available(sv: "ShardedVector") -> bool:
     """Peer-memory exchange needs CUDA shards, more than one rank, at most 16 of them on one box with
     symmetric memory working; the decision is taken collectively so that all ranks agree."""
     if sv.world == 1 or sv.world > 16 or not sv.device.type == "cuda":
         return False
-    # FFSIM_B200_EXCHANGE: "nccl" = never, "p2p" = whenever symmetric memory works, "auto" (default) =
-    # only in the configuration it has been validated in (two ranks).  An 8-rank run of the 254 GB state
-    # with 32 GB symmetric buffers did not complete within the time limit of the last GPU slot of round 1,
-    # so beyond two ranks the NCCL all-to-all (measured at 8 ranks) stays the default until that is understood.
     mode = os.environ.get("FFSIM_B200_EXCHANGE", "auto").lower()
-    if mode == "nccl" or (mode != "p2p" and sv.world > 2):
+    max_world = int(os.environ.get("FFSIM_B200_P2P_MAX_WORLD", "2"))
+    if mode == "nccl" or (mode != "p2p" and sv.world > max_world):
         return False
     if not _SYMM_STATE["checked"]:
         ok = 1
@@ -289,93 +385,111 @@ def p2p_available(sv: "ShardedVector") -> bool:
     return _SYMM_STATE["ok"]
 
 
-def _i64(values):
-    return (ctypes.c_int64 * len(values))(*[int(v) for v in values])
+def _symm_numel(sv: ShardedVector) -> int:
+    """One size for both distributions (so that the pool hands the same buffers back and forth)."""
+    rows_max = max(sv.a_off[r + 1] - sv.a_off[r] for r in range(sv.world))
+    cols_max = max(sv.b_off[r + 1] - sv.b_off[r] for r in range(sv.world))
+    return max(rows_max * sv.dim_b, sv.dim_a * cols_max, 1)
 
 
-def _exchange(src: torch.Tensor, src_ld: int, rows, width, src_off, dst_ptrs, dst_off, dst_ld) -> None:
-    from ffsim_b200 import _device, _lib
-
-    n = len(rows)
-    ptrs = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(p)) for p in dst_ptrs])
-    _lib.check(_lib.lib.ffb_exchange_blocks(
-        src.data_ptr(), int(src_ld), n, _i64(rows), _i64(width), _i64(src_off), ptrs, _i64(dst_off), _i64(dst_ld),
-        _device.stream_ptr()))
-
-
-def _make_symmetric(sv: "ShardedVector") -> _SymmBuffer:
-    """Move the row shard into symmetric memory (once per vector; it stays there)."""
-    buf = getattr(sv, "_symm", None)
+def _make_symmetric(sv: ShardedVector) -> _SymmBuffer:
+    """Move the shard into symmetric memory (once per vector; it stays there)."""
+    buf = sv._symm
     if buf is not None and sv.local is not None and sv.local.data_ptr() == buf.tensor.data_ptr():
         return buf
-    numel = max(max(sv.a_off[r + 1] - sv.a_off[r] for r in range(sv.world)) * sv.dim_b, 1)
-    buf = _symm_get(numel, sv.device, sv.group)
-    view = buf.tensor[: sv.n_rows * sv.dim_b]
+    buf = _symm_get(_symm_numel(sv), sv.device, sv.group)
+    view = buf.tensor[: sv.local.numel()]
     view.copy_(sv.local)
-    sv.local = view
-    sv._symm = buf
-    weakref.finalize(sv, _symm_put, buf, sv.device, sv.group)
+    sv._adopt(view, sv.layout, buf)
     return buf
 
 
-def rotate_alpha_p2p(sv: "ShardedVector", plan, stream) -> None:
-    """Alpha-side rotation through peer memory: scatter the row shard into every rank's column shard,
-    rotate locally, scatter back.  Two kernels move data; nothing is packed, staged or unpacked."""
-    from ffsim_b200 import _lib
+def _redistribute_p2p(sv: ShardedVector, layout: str) -> None:
+    """One kernel: every rank stores its blocks straight into their final place in the peers' shards."""
+    src_buf = _make_symmetric(sv)
+    dst_buf = _symm_get(_symm_numel(sv), sv.device, sv.group)
+    with torch.cuda.device(sv.device):
+        dst_buf.handle.barrier(channel=0)  # peers may still be reading this buffer from an earlier exchange
+        if layout == COLS:
+            g = _row_block_geometry(sv)
+            _copy_blocks(sv.local, sv.dim_b, g["rows"], g["width"], g["row_off"], dst_buf.ptrs, g["col_off"], g["col_ld"])
+        else:
+            g = _col_block_geometry(sv)
+            _copy_blocks(sv.local, sv.n_cols, g["rows"], g["width"], g["col_off"], dst_buf.ptrs, g["row_off"], g["row_ld"])
+        dst_buf.handle.barrier(channel=0)
+    del src_buf  # _adopt hands the old buffer back to the pool
+    sv._adopt(dst_buf.tensor[: sv.local_numel(layout)], layout, dst_buf)
 
-    w, r = sv.world, sv.rank
-    rows_of = [sv.a_off[d + 1] - sv.a_off[d] for d in range(w)]
-    cols_of = [sv.b_off[d + 1] - sv.b_off[d] for d in range(w)]
-    nb_local = cols_of[r]
-    row_buf = _make_symmetric(sv)
-    col_numel = max(sv.dim_a * max(cols_of), 1)
-    col_buf = _symm_get(col_numel, sv.device, sv.group)
-    try:
-        # every rank may still be reading its column buffer from an earlier exchange
-        col_buf.handle.barrier(channel=0)
-        # row shard -> column shards: block d = my rows x d's columns, lands at my row offset of d's buffer
-        _exchange(sv.local, sv.dim_b, [sv.n_rows] * w, cols_of, [sv.b_off[d] for d in range(w)],
-                  col_buf.ptrs, [sv.a_off[r] * cols_of[d] for d in range(w)], cols_of)
-        col_buf.handle.barrier(channel=0)
-        if nb_local > 0:
-            _lib.check(_lib.lib.ffb_apply_orbital_rotation_rows(
-                plan.handle, 0, col_buf.tensor.data_ptr(), nb_local, nb_local, stream))
-        # column shard -> row shards: block d = d's rows x my columns, lands at my column offset of d's shard
-        _exchange(col_buf.tensor, nb_local, rows_of, [nb_local] * w, [sv.a_off[d] * nb_local for d in range(w)],
-                  row_buf.ptrs, [sv.b_off[r]] * w, [sv.dim_b] * w)
-        col_buf.handle.barrier(channel=0)
-    finally:
-        _symm_put(col_buf, sv.device, sv.group)
+
+def redistribute(sv: ShardedVector, layout: str) -> None:
+    """Move ``sv`` to the other distribution (collective)."""
+    if layout == sv.layout:
+        return
+    STATS["exchanges"] += 1
+    STATS["bytes_sent"] += all_to_all_bytes(sv)
+    if sv.world == 1:
+        # one rank: both distributions are the whole matrix
+        sv.layout = layout
+        return
+    if p2p_available(sv):
+        _redistribute_p2p(sv, layout)
+    elif layout == COLS:
+        _rows_to_cols_a2a(sv)
+    else:
+        _cols_to_rows_a2a(sv)
 
 
 # ---------------------------------------------------------------------- device ops on shards
 
+def _rotate_beta_local(sv: ShardedVector, plan, stream) -> None:
+    """Beta-side rotation of the rows-distribution shard: the contiguous index of the local rows."""
+    from ffsim_b200 import _lib
+
+    if sv.n_rows == 0:
+        return
+    if _lib.lib.ffb_plan_beta_in_place(plan.handle):
+        _lib.check(_lib.lib.ffb_apply_orbital_rotation_strided(
+            plan.handle, 1, sv.local.data_ptr(), sv.n_rows, 1, sv.dim_b, stream))
+        return
+    ws = torch.empty(sv.dim_b * sv.n_rows, dtype=torch.complex128, device=sv.device)
+    _lib.check(_lib.lib.ffb_transpose(sv.local.data_ptr(), ws.data_ptr(), sv.n_rows, sv.dim_b,
+                                      sv.dim_b, sv.n_rows, stream))
+    _lib.check(_lib.lib.ffb_apply_orbital_rotation_rows(plan.handle, 1, ws.data_ptr(), sv.n_rows, sv.n_rows, stream))
+    _lib.check(_lib.lib.ffb_transpose(ws.data_ptr(), sv.local.data_ptr(), sv.dim_b, sv.n_rows,
+                                      sv.n_rows, sv.dim_b, stream))
+
+
+def _rotate_alpha_local(sv: ShardedVector, plan, stream) -> None:
+    """Alpha-side rotation of the cols-distribution shard: the row index of a [dim_a x n_cols] matrix."""
+    from ffsim_b200 import _lib
+
+    if sv.n_cols > 0:
+        _lib.check(_lib.lib.ffb_apply_orbital_rotation_rows(
+            plan.handle, 0, sv.local.data_ptr(), sv.n_cols, sv.n_cols, stream))
+
+
 def rotate(sv: ShardedVector, mat_a, mat_b) -> None:
-    """Orbital rotation of a sharded state, in place (both spin sectors)."""
-    from ffsim_b200 import _device, _lib
+    """Orbital rotation of a sharded state, in place (both spin sectors).  The spin sector that is local
+    in the current distribution goes first (the two commute); the other one follows after ONE
+    redistribution, and the state stays in that distribution."""
+    from ffsim_b200 import _device
     from ffsim_b200.gates.orbital_rotation import get_plan
 
     with torch.cuda.device(sv.device):
         plan = get_plan(sv.norb, sv.nelec, mat_a, mat_b)
         stream = _device.stream_ptr()
-        if mat_b is not None and sv.n_rows > 0:
-            if _lib.lib.ffb_plan_beta_in_place(plan.handle):
-                _lib.check(_lib.lib.ffb_apply_orbital_rotation_strided(
-                    plan.handle, 1, sv.local.data_ptr(), sv.n_rows, 1, sv.dim_b, stream))
-            else:
-                ws = torch.empty(sv.dim_b * sv.n_rows, dtype=torch.complex128, device=sv.device)
-                _lib.check(_lib.lib.ffb_transpose(sv.local.data_ptr(), ws.data_ptr(), sv.n_rows, sv.dim_b,
-                                                  sv.dim_b, sv.n_rows, stream))
-                _lib.check(_lib.lib.ffb_apply_orbital_rotation_rows(
-                    plan.handle, 1, ws.data_ptr(), sv.n_rows, sv.n_rows, stream))
-                _lib.check(_lib.lib.ffb_transpose(ws.data_ptr(), sv.local.data_ptr(), sv.dim_b, sv.n_rows,
-                                                  sv.n_rows, sv.dim_b, stream))
-        if mat_a is not None and p2p_available(sv):
-            rotate_alpha_p2p(sv, plan, stream)
-        elif mat_a is not None:
-            cols = to_column_shards(sv, release=True)
-            nb_local = cols.shape[1]
-            if nb_local > 0:
-                _lib.check(_lib.lib.ffb_apply_orbital_rotation_rows(
-                    plan.handle, 0, cols.data_ptr(), nb_local, nb_local, stream))
-            from_column_shards(sv, cols)
+        if sv.world == 1:
+            # one rank holds everything: both sides are local, no need to flip the label
+            if mat_b is not None:
+                _rotate_beta_local(sv, plan, stream)
+            if mat_a is not None:
+                _rotate_alpha_local(sv, plan, stream)
+            return
+        order = ("b", "a") if sv.layout == ROWS else ("a", "b")
+        for side in order:
+            if side == "b" and mat_b is not None:
+                sv.set_layout(ROWS)
+                _rotate_beta_local(sv, plan, stream)
+            elif side == "a" and mat_a is not None:
+                sv.set_layout(COLS)
+                _rotate_alpha_local(sv, plan, stream)

@@ -54,13 +54,14 @@ def _get_mat_exp(mat: Any, time: float, norb: int, z_representation: bool):
 def _evolve_device(t, mats, norb: int, nelec: tuple[int, int], z_representation: bool) -> None:
     aa, ab, bb = mats
     ta, tb = get_tables(norb, nelec[0]), get_tables(norb, nelec[1])
-    data, row0, n_rows = _device.local_block(t, ta.dim)
+    data, row0, n_rows, col0, n_cols, ld = _device.local_block(t, ta.dim, tb.dim)
     with torch.cuda.device(data.device):
         _device.sync_device()
         _lib.check(
-            _lib.lib.ffb_apply_diag_coulomb_evolution(
+            _lib.lib.ffb_apply_diag_coulomb_evolution_block(
                 ta.handle, tb.handle, _lib.ptr(aa), _lib.ptr(ab), _lib.ptr(bb),
-                int(bool(z_representation)), data.data_ptr(), row0, n_rows, _device.stream_ptr(),
+                int(bool(z_representation)), data.data_ptr(), row0, n_rows, col0, n_cols, ld,
+                _device.stream_ptr(),
             )
         )
 

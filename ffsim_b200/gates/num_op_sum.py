@@ -32,13 +32,13 @@ def _get_phases(coeffs, time: float):
 
 def _evolve_device(t, phases_a, phases_b, norb: int, nelec: tuple[int, int]) -> None:
     ta, tb = get_tables(norb, nelec[0]), get_tables(norb, nelec[1])
-    data, row0, n_rows = _device.local_block(t, ta.dim)
+    data, row0, n_rows, col0, n_cols, ld = _device.local_block(t, ta.dim, tb.dim)
     with torch.cuda.device(data.device):
         _device.sync_device()
         _lib.check(
-            _lib.lib.ffb_apply_num_op_sum_evolution(
+            _lib.lib.ffb_apply_num_op_sum_evolution_block(
                 ta.handle, tb.handle, _lib.ptr(phases_a), _lib.ptr(phases_b), data.data_ptr(), row0, n_rows,
-                _device.stream_ptr(),
+                col0, n_cols, ld, _device.stream_ptr(),
             )
         )
 

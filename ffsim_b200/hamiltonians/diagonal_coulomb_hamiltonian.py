@@ -21,6 +21,7 @@ from ffsim_b200.states import dim
 def axpby(alpha: complex, x, beta: complex, y) -> None:
     """y = alpha * x + beta * y on the device (tensors or ShardedVectors)."""
     if _device.is_sharded(x):
+        _device.same_layout(x, y)  # y follows x's distribution (a redistribution only when they differ)
         x, y = x.local, y.local
     if x.numel() == 0:
         return

@@ -153,22 +153,24 @@ def simulate_qdrift_double_factorized(
     for _ in range(n_samples):
         t = initial.clone()
         term_indices = rng.choice(len(probabilities), size=n_steps, replace=True, p=probabilities)
-        basis = eye  # the orbital basis the device vector is currently expressed in
+        basis, basis_id = eye, -1  # the orbital basis the device vector is currently expressed in
 
-        def to_basis(new_basis):
-            nonlocal basis
-            if new_basis is not basis:
+        def to_basis(new_basis, new_id):
+            # bases are tracked by term index (-1 identity, 0 one-body eigenbasis, k two-body term k):
+            # two consecutive samples of the same term must not cost a rotation by the identity
+            nonlocal basis, basis_id
+            if new_id != basis_id:
                 u = new_basis.T.conj() @ basis
                 _rotate_device(t, u, u, norb, nelec)
-                basis = new_basis
+                basis, basis_id = new_basis, new_id
 
         def one_body(term_time):
-            to_basis(basis_change)
+            to_basis(basis_change, 0)
             phases = np.ascontiguousarray(np.exp(-1j * term_time * energies))
             _evolve_num_op_sum(t, phases, phases, norb, nelec)
 
         def two_body(index, term_time):
-            to_basis(np.asarray(hamiltonian.orbital_rotations[index - 1]))
+            to_basis(np.asarray(hamiltonian.orbital_rotations[index - 1]), int(index))
             mats = _get_mat_exp(np.asarray(hamiltonian.diag_coulomb_mats[index - 1]), term_time, norb, z_rep)
             _evolve_device(t, mats, norb, nelec, z_rep)
 
@@ -185,6 +187,6 @@ def simulate_qdrift_double_factorized(
                     one_body(step_time / probabilities[0])
                 else:
                     two_body(index, step_time / probabilities[index])
-        to_basis(eye)
+        to_basis(eye, -1)
         samples.append(t)
     return finish(samples)

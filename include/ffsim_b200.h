@@ -180,6 +180,30 @@ int ffb_contract_num_op_sum(ffb_tables *tables_a, ffb_tables *tables_b, const do
                             const double *coeffs_b, const void *vec_dev, void *out_dev,
                             int accumulate, int64_t row0, int64_t n_rows, void *stream);
 
+/* The same four operators on a rectangular block of the state: alpha rows [row0, row0 + n_rows) x
+ * beta columns [col0, col0 + n_cols), element (row0 + r, col0 + c) at vec_dev[r * ld + c].  n_cols < 0
+ * means the whole beta sector with contiguous rows (the calls above).  A column block is what a
+ * rank holds after the distributed transpose (the state stays in that layout
+ * between an alpha-side rotation and the next one, diagonal operators work on either). */
+int ffb_apply_diag_coulomb_evolution_block(ffb_tables *tables_a, ffb_tables *tables_b,
+                                           const ffb_c128 *mat_exp_aa, const ffb_c128 *mat_exp_ab,
+                                           const ffb_c128 *mat_exp_bb, int z_representation,
+                                           void *vec_dev, int64_t row0, int64_t n_rows, int64_t col0,
+                                           int64_t n_cols, int64_t ld, void *stream);
+int ffb_apply_num_op_sum_evolution_block(ffb_tables *tables_a, ffb_tables *tables_b,
+                                         const ffb_c128 *phases_a, const ffb_c128 *phases_b,
+                                         void *vec_dev, int64_t row0, int64_t n_rows, int64_t col0,
+                                         int64_t n_cols, int64_t ld, void *stream);
+int ffb_contract_diag_coulomb_block(ffb_tables *tables_a, ffb_tables *tables_b, const double *mat_aa,
+                                    const double *mat_ab, const double *mat_bb, int z_representation,
+                                    const void *vec_dev, void *out_dev, int accumulate, int64_t row0,
+                                    int64_t n_rows, int64_t col0, int64_t n_cols, int64_t ld,
+                                    void *stream);
+int ffb_contract_num_op_sum_block(ffb_tables *tables_a, ffb_tables *tables_b, const double *coeffs_a,
+                                  const double *coeffs_b, const void *vec_dev, void *out_dev,
+                                  int accumulate, int64_t row0, int64_t n_rows, int64_t col0,
+                                  int64_t n_cols, int64_t ld, void *stream);
+
 /* ---------------------------------------------------------------- utilities */
 /* out[c, r] = in[r, c]; in is n_rows x n_cols with row stride ld_in, out has row stride ld_out. */
 int ffb_transpose(const void *in_dev, void *out_dev, int64_t n_rows, int64_t n_cols, int64_t ld_in,
@@ -193,6 +217,11 @@ int ffb_transpose(const void *in_dev, void *out_dev, int64_t n_rows, int64_t n_c
 int ffb_exchange_blocks(const void *src_dev, int64_t src_ld, int n_dst, const int64_t *rows,
                         const int64_t *width, const int64_t *src_off, void *const *dst_dev,
                         const int64_t *dst_off, const int64_t *dst_ld, void *stream);
+/* The same kernel with one source row stride per block: the pack / unpack step of the NCCL
+ * all-to-all path (all destinations local) as well as the peer-memory exchange. */
+int ffb_copy_blocks(const void *src_dev, int n_blocks, const int64_t *rows, const int64_t *width,
+                    const int64_t *src_off, const int64_t *src_ld, void *const *dst_dev,
+                    const int64_t *dst_off, const int64_t *dst_ld, void *stream);
 /* result_dev[0] = sum conj(x) * y as one complex128 (device scalar, 16 bytes). */
 int ffb_vdot(const void *x_dev, const void *y_dev, int64_t n, void *result_dev, void *stream);
 /* y = alpha * x + beta * y, complex scalars */

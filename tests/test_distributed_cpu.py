@@ -19,7 +19,7 @@ WORKER = r'''
 import sys, math
 sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
-from ffsim_b200.distributed import ShardedVector, partition, to_column_shards, from_column_shards, all_to_all_bytes
+from ffsim_b200.distributed import ShardedVector, partition, all_to_all_bytes, STATS, ROWS, COLS
 from oracle import gates, givens, rand, models, cistring
 
 dist.init_process_group("gloo")
@@ -37,15 +37,27 @@ for norb, nelec in [(5, (2, 3)), (6, (3, 3)), (4, (1, 4)), (3, (0, 2))]:
     other = ShardedVector.from_global(full[::-1].copy(), norb, nelec)
     assert abs(sv.vdot(other) - np.vdot(full, full[::-1])) < 1e-13
     # redistribution: column shard == the global matrix restricted to this rank's columns
-    cols = to_column_shards(sv)
     b0, b1 = sv.b_off[rank], sv.b_off[rank + 1]
-    assert cols.shape == (dim_a, b1 - b0)
-    assert np.array_equal(cols.numpy(), full.reshape(dim_a, dim_b)[:, b0:b1])
     assert all_to_all_bytes(sv) == 16 * sv.n_rows * (dim_b - (b1 - b0))
+    n_ex = STATS["exchanges"]
+    sv.set_layout(COLS)
+    assert sv.layout == COLS and STATS["exchanges"] == n_ex + 1
+    cols = sv.local.view(dim_a, b1 - b0)
+    assert np.array_equal(cols.numpy(), full.reshape(dim_a, dim_b)[:, b0:b1])
+    blk = sv.block()
+    assert blk[1:] == (0, dim_a, b0, b1 - b0, b1 - b0)
+    assert all_to_all_bytes(sv) == 16 * (dim_a - sv.n_rows) * (b1 - b0)
+    # scalars work in either distribution (the other operand follows)
+    assert abs(sv.norm() - 1.0) < 1e-13
+    assert abs(sv.vdot(other) - np.vdot(full, full[::-1])) < 1e-13 and other.layout == COLS
     # alpha rotation on the column shard (oracle compute), then back
     work = np.ascontiguousarray(cols.numpy())
     gates._rotate_one_spin(work, givens.givens_decomposition(ua), norb, nelec[0])
-    from_column_shards(sv, torch.from_numpy(work))
+    sv.local.copy_(torch.from_numpy(work).reshape(-1))
+    sv.set_layout(COLS)  # no-op
+    assert STATS["exchanges"] == n_ex + 2  # (the vdot moved `other`)
+    sv.set_layout(ROWS)
+    assert sv.block()[1:] == (sv.row0, sv.n_rows, 0, dim_b, dim_b)
     # beta rotation is local to the row shard
     loc = np.ascontiguousarray(sv.local.numpy().reshape(sv.n_rows, dim_b).T)
     gates._rotate_one_spin(loc, givens.givens_decomposition(ub), norb, nelec[1])
