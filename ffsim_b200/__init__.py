@@ -23,7 +23,25 @@ from ffsim_b200.trotter import (
 )
 from ffsim_b200.variational import UCJOpSpinBalanced, UCJOpSpinless, UCJOpSpinUnbalanced
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+
+def to_device(vec):
+    """Upload a host vector (NumPy array or CPU tensor) once: a 1-D ``complex128`` CUDA tensor that the
+    functions of this package update in place with ``copy=False``.  Pinned host memory goes straight to
+    the DMA engine; pageable memory is staged through a pooled pinned buffer."""
+    from ffsim_b200 import _device
+
+    return _device.to_device(vec, copy=True)[0]
+
+
+def to_host(t):
+    """Download a CUDA tensor produced by this package: a NumPy array over (pooled) pinned memory."""
+    from ffsim_b200 import _device
+
+    if _device.is_sharded(t):
+        raise TypeError("to_host: pass the shard (ShardedVector.local), not the distributed vector")
+    return _device._download(t.reshape(-1))
 
 __all__ = [
     "DiagonalCoulombHamiltonian",
@@ -51,4 +69,6 @@ __all__ = [
     "simulate_qdrift_double_factorized",
     "simulate_trotter_diag_coulomb_split_op",
     "simulate_trotter_double_factorized",
+    "to_device",
+    "to_host",
 ]

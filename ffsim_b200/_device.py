@@ -6,6 +6,7 @@ state happens in libffsim_b200.so.
 
 from __future__ import annotations
 
+import os
 import threading
 import weakref
 from typing import Any
@@ -105,7 +106,7 @@ _STAGE_MIN_BYTES = 1 << 20
 
 _POOL: dict[int, list[torch.Tensor]] = {}
 _POOL_LOCK = threading.Lock()
-_POOL_MAX_BYTES = 8 << 30  # free pinned memory kept around
+_POOL_MAX_BYTES = int(os.environ.get("FFSIM_B200_PINNED_POOL_GB", "48")) << 30  # free pinned memory kept around
 _pool_bytes = 0
 
 

@@ -102,6 +102,7 @@ EXPORTS = {
     "ffb_axpby": (c_int, C128, _P, C128, _P, c_int64, _P),
     "ffb_profile_begin": (c_int,),
     "ffb_profile_end": (c_int, c_char_p, c_size_t),
+    "ffb_measure_fp64_peak": (c_int, POINTER(c_double)),
     "ffb_set_option": (c_int, c_char_p, c_int64),
     "ffb_get_option": (c_int64, c_char_p),
 }
@@ -150,6 +151,13 @@ def profile_end() -> dict:
     buf = ctypes.create_string_buffer(4096)
     check(lib.ffb_profile_end(buf, len(buf)))
     return json.loads(buf.value.decode())
+
+
+def measure_fp64_peak() -> float:
+    """Dense DFMA throughput of the current device (TFLOP/s), measured now."""
+    out = c_double(0.0)
+    check(lib.ffb_measure_fp64_peak(byref(out)))
+    return float(out.value)
 
 
 def set_option(key: str, value: int) -> None:

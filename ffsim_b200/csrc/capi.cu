@@ -53,7 +53,7 @@ struct ProfState {
   struct Rec {
     cudaEvent_t a, b;
     int kind;
-    double bytes;
+    double bytes, dfma;
   };
   std::vector<Rec> recs;
   long long launches[kProfKinds] = {0, 0, 0, 0, 0};
@@ -64,9 +64,10 @@ struct ProfScope {
   cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
   int kind;
-  double bytes;
+  double bytes, dfma;
   bool on;
-  ProfScope(int kind_, double bytes_, cudaStream_t st_) : st(st_), kind(kind_), bytes(bytes_) {
+  ProfScope(int kind_, double bytes_, cudaStream_t st_, double dfma_ = 0.0)
+      : st(st_), kind(kind_), bytes(bytes_), dfma(dfma_) {
     g_prof.launches[kind] += 1;
     on = g_prof.enabled && kind != kProfOther;
     if (on) {
@@ -79,7 +80,7 @@ struct ProfScope {
     if (on) {
       cudaEventRecord(b, st);
       std::lock_guard<std::mutex> lk(g_prof.mu);
-      g_prof.recs.push_back({a, b, kind, bytes});
+      g_prof.recs.push_back({a, b, kind, bytes, dfma});
     }
   }
 };
@@ -379,7 +380,9 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     const int ctas_per_sm = fused_pass_ctas_per_sm(P.w, plan->opt.threads, tile_bytes + overhead);
     const int grid = (int)std::min<long long>(units, (long long)plan->dev.sm_count * ctas_per_sm);
     {
-      ProfScope prof(kProfFused, 32.0 * (double)dim * (double)n_cols, stream);
+      // FP64-pipe work of the pass: 4 DMUL + 8 DFMA per rotation and amplitude pair
+      const double pairs = (double)binom(sp.tables->norb - 2, sp.tables->nocc - 1) * (double)n_cols;
+      ProfScope prof(kProfFused, 32.0 * (double)dim * (double)n_cols, stream, 12.0 * P.n_rot * pairs);
       FFB_CUDA(launch_fused_pass(P, grid, plan->opt.threads, tile_bytes + overhead, stream));
     }
   }
@@ -849,13 +852,14 @@ int ffb_profile_end(char *buf, size_t buflen) {
   FFB_CUDA(cudaDeviceSynchronize());
   std::lock_guard<std::mutex> lk(g_prof.mu);
   g_prof.enabled = false;
-  double ms[kProfKinds] = {0, 0, 0, 0, 0}, bytes[kProfKinds] = {0, 0, 0, 0, 0};
+  double ms[kProfKinds] = {0, 0, 0, 0, 0}, bytes[kProfKinds] = {0, 0, 0, 0, 0}, dfma[kProfKinds] = {0, 0, 0, 0, 0};
   long long timed[kProfKinds] = {0, 0, 0, 0, 0};
   for (auto &r : g_prof.recs) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
       ms[r.kind] += t;
       bytes[r.kind] += r.bytes;
+      dfma[r.kind] += r.dfma;
       timed[r.kind] += 1;
     }
     cudaEventDestroy(r.a);
@@ -867,10 +871,22 @@ int ffb_profile_end(char *buf, size_t buflen) {
   os << "{";
   for (int k = 0; k < kProfKinds; ++k) {
     os << (k ? ", " : "") << "\"" << kProfNames[k] << "\": {\"launches\": " << g_prof.launches[k]
-       << ", \"timed\": " << timed[k] << ", \"ms\": " << ms[k] << ", \"bytes\": " << bytes[k] << "}";
+       << ", \"timed\": " << timed[k] << ", \"ms\": " << ms[k] << ", \"bytes\": " << bytes[k]
+       << ", \"dfma_ops\": " << dfma[k] << "}";
   }
   os << "}";
   std::snprintf(buf, buflen, "%s", os.str().c_str());
+  return FFB_OK;
+}
+
+int ffb_measure_fp64_peak(double *tflops) {
+  if (!tflops) return fail(FFB_EINVAL, "ffb_measure_fp64_peak: NULL argument");
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc != FFB_OK) return rc;
+  double best = 0.0;
+  FFB_CUDA(measure_fp64_peak(di.sm_count, &best));
+  *tflops = best;
   return FFB_OK;
 }
 

@@ -12,6 +12,8 @@
 // filled (conjugate / sign selected by the string bits over all orbitals).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "kernels.hpp"
 
 namespace ffb {
@@ -276,6 +278,22 @@ __global__ void axpby_kernel(double ar, double ai, const double2 *__restrict__ x
   }
 }
 
+// sixteen independent DFMA chains per thread, coefficients in the constant bank: the operand pattern
+// of the rotation kernel's inner loop (scripts/micro/fp64_peak.cu measured the same number)
+__global__ void __launch_bounds__(1024) fp64_peak_kernel(double *out, double a, double b, int iters) {
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 1e-9 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = fma(x[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 12345.678) out[0] = s;
+}
+
 int grid_1d(long long total, int threads, int sm_count, int per_sm) {
   long long blocks = (total + threads - 1) / threads;
   long long cap = (long long)sm_count * per_sm;
@@ -345,6 +363,32 @@ cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t
   if (contract) return rpw == 2 ? launch(diag_kernel<Re, true, 2, 2>) : launch(diag_kernel<Re, true, 1, 4>);
   if (rpw == 2) return one_wave ? launch(diag_kernel<Cx, false, 2, 4>) : launch(diag_kernel<Cx, false, 2, 2>);
   return launch(diag_kernel<Cx, false, 1, 4>);
+}
+
+cudaError_t measure_fp64_peak(int sm_count, double *tflops) {
+  double *out = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(double));
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 4000, threads = 1024, blocks = sm_count * 2;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {  // the first launch warms the clocks up
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(out, 1.0000001, 1e-9, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 16.0 * (double)iters * threads * (double)blocks;
+    if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_vdot(const void *x, const void *y, long long n, void *partial, int n_partial,

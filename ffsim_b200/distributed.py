@@ -53,8 +53,9 @@ def partition(n: int, world: int) -> list[int]:
 
 ROWS, COLS = "rows", "cols"
 
-# counters of the redistribution (bench.py / tests read them): exchanges done and bytes this rank sent
-STATS = {"exchanges": 0, "bytes_sent": 0}
+# counters of the redistribution (bench.py / tests read them): exchanges done, bytes this rank sent, the
+# implementation used ("p2p" / "nccl") and, when "time" is set, a CUDA event pair around every exchange
+STATS = {"exchanges": 0, "bytes_sent": 0, "mode": None, "time": False, "events": []}
 
 
 class ShardedVector:
@@ -431,12 +432,22 @@ def redistribute(sv: ShardedVector, layout: str) -> None:
         # one rank: both distributions are the whole matrix
         sv.layout = layout
         return
+    timed = STATS.get("time") and sv.device.type == "cuda"
+    if timed:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     if p2p_available(sv):
+        STATS["mode"] = "p2p"
         _redistribute_p2p(sv, layout)
-    elif layout == COLS:
-        _rows_to_cols_a2a(sv)
     else:
-        _cols_to_rows_a2a(sv)
+        STATS["mode"] = "nccl"
+        if layout == COLS:
+            _rows_to_cols_a2a(sv)
+        else:
+            _cols_to_rows_a2a(sv)
+    if timed:
+        ev[1].record()
+        STATS["events"].append(ev)
 
 
 # ---------------------------------------------------------------------- device ops on shards

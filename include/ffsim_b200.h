@@ -235,6 +235,10 @@ int ffb_axpby(ffb_c128 alpha, const void *x_dev, ffb_c128 beta, void *y_dev, int
 int ffb_profile_begin(void);
 int ffb_profile_end(char *buf, size_t buflen);
 
+/* Dense FP64 FMA throughput of the current device in TFLOP/s (a short microbenchmark, ~10 ms): the
+ * second roofline denominator of the fused rotation kernel, measured where the bench runs. */
+int ffb_measure_fp64_peak(double *tflops);
+
 /* Tuning knobs (process-wide; read when a plan is built).  key/value pairs:
  *   "smem_bytes"   shared-memory budget per tile (default: device opt-in max)
  *   "min_cols"     smallest column strip per tile (default 4)
