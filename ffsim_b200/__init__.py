@@ -10,18 +10,38 @@ state runs in hand-written sm_100a CUDA kernels behind the C ABI of
 from ffsim_b200 import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
 from ffsim_b200 import contract, linalg, random
 from ffsim_b200.contract import contract_diag_coulomb, contract_num_op_sum, diag_coulomb_linop, num_op_sum_linop
-from ffsim_b200.gates import apply_diag_coulomb_evolution, apply_num_op_sum_evolution, apply_orbital_rotation
+from ffsim_b200.gates import (
+    apply_diag_coulomb_evolution,
+    apply_fsim_gate,
+    apply_fswap_gate,
+    apply_givens_rotation,
+    apply_hop_gate,
+    apply_num_interaction,
+    apply_num_num_interaction,
+    apply_num_op_prod_interaction,
+    apply_num_op_sum_evolution,
+    apply_on_site_interaction,
+    apply_orbital_rotation,
+    apply_tunneling_interaction,
+)
 from ffsim_b200.hamiltonians import DiagonalCoulombHamiltonian, DoubleFactorizedHamiltonian
 from ffsim_b200.init_cache import init_cache
 from ffsim_b200.protocols import apply_unitary, linear_operator
-from ffsim_b200.states import dim, dims, hartree_fock_state
+from ffsim_b200.states import Spin, dim, dims, hartree_fock_state
 from ffsim_b200.trotter import (
     qdrift_probabilities,
     simulate_qdrift_double_factorized,
     simulate_trotter_diag_coulomb_split_op,
     simulate_trotter_double_factorized,
 )
-from ffsim_b200.variational import UCJOpSpinBalanced, UCJOpSpinless, UCJOpSpinUnbalanced
+from ffsim_b200.variational import (
+    GivensAnsatzOp,
+    NumNumAnsatzOpSpinBalanced,
+    UCJAnglesOpSpinBalanced,
+    UCJOpSpinBalanced,
+    UCJOpSpinless,
+    UCJOpSpinUnbalanced,
+)
 
 __version__ = "0.2.0"
 
@@ -46,12 +66,25 @@ def to_host(t):
 __all__ = [
     "DiagonalCoulombHamiltonian",
     "DoubleFactorizedHamiltonian",
+    "GivensAnsatzOp",
+    "NumNumAnsatzOpSpinBalanced",
+    "Spin",
+    "UCJAnglesOpSpinBalanced",
     "UCJOpSpinBalanced",
     "UCJOpSpinUnbalanced",
     "UCJOpSpinless",
     "apply_diag_coulomb_evolution",
+    "apply_fsim_gate",
+    "apply_fswap_gate",
+    "apply_givens_rotation",
+    "apply_hop_gate",
+    "apply_num_interaction",
+    "apply_num_num_interaction",
+    "apply_num_op_prod_interaction",
     "apply_num_op_sum_evolution",
+    "apply_on_site_interaction",
     "apply_orbital_rotation",
+    "apply_tunneling_interaction",
     "apply_unitary",
     "contract",
     "contract_diag_coulomb",

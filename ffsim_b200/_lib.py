@@ -95,6 +95,8 @@ EXPORTS = {
     "ffb_apply_num_op_sum_evolution_block": (c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P),
     "ffb_contract_diag_coulomb_block": (c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, _P),
     "ffb_contract_num_op_sum_block": (c_int, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, _P),
+    "ffb_apply_num_op_prod_phase": (c_int, _P, _P, ctypes.c_uint32, ctypes.c_uint32, C128, _P, c_int64, c_int64, c_int64,
+                                    c_int64, c_int64, _P),
     "ffb_transpose": (c_int, _P, _P, c_int64, c_int64, c_int64, c_int64, _P),
     "ffb_exchange_blocks": (c_int, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P),
     "ffb_copy_blocks": (c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P),

@@ -169,12 +169,16 @@ int get_structure(int norb, int nocc, const std::vector<int> &q, const PlanOptio
     return FFB_OK;
   }
   std::shared_ptr<SideStructure> st(new SideStructure());
-  st->sched = build_schedule(norb, nocc, q, opt);
-  for (const PassSchedule &ps : st->sched.passes) {
-    std::unique_ptr<DevicePass> dp;
-    int rc = build_device_pass(norb, nocc, ps, &dp);
-    if (rc != FFB_OK) return rc;
-    st->passes.push_back(std::move(dp));
+  try {
+    st->sched = build_schedule(norb, nocc, q, opt);
+    for (const PassSchedule &ps : st->sched.passes) {
+      std::unique_ptr<DevicePass> dp;
+      int rc = build_device_pass(norb, nocc, ps, &dp);
+      if (rc != FFB_OK) return rc;
+      st->passes.push_back(std::move(dp));
+    }
+  } catch (const std::exception &e) {  // plan-builder invariants (plan.cpp) and allocation failures
+    return fail(FFB_EINTERNAL, e.what());
   }
   if (g_cache.size() > 64) g_cache.clear();  // bounded; live plans keep their own references
   g_cache[key.str()] = st;
@@ -876,6 +880,32 @@ int ffb_profile_end(char *buf, size_t buflen) {
   }
   os << "}";
   std::snprintf(buf, buflen, "%s", os.str().c_str());
+  return FFB_OK;
+}
+
+int ffb_apply_num_op_prod_phase(ffb_tables *tables_a, ffb_tables *tables_b, uint32_t mask_a, uint32_t mask_b,
+                                ffb_c128 phase, void *vec_dev, int64_t row0, int64_t n_rows, int64_t col0,
+                                int64_t n_cols, int64_t ld, void *stream) {
+  if (!tables_a || !tables_b) return fail(FFB_EINVAL, "ffb_apply_num_op_prod_phase: NULL tables");
+  if (row0 < 0 || n_rows < 0 || row0 + n_rows > tables_a->dim)
+    return fail(FFB_EINVAL, "ffb_apply_num_op_prod_phase: row block outside the alpha sector");
+  if (n_cols < 0) {
+    col0 = 0;
+    n_cols = tables_b->dim;
+    ld = tables_b->dim;
+  }
+  if (col0 < 0 || col0 + n_cols > tables_b->dim || ld < n_cols)
+    return fail(FFB_EINVAL, "ffb_apply_num_op_prod_phase: column block outside the beta sector");
+  if (n_rows == 0 || n_cols == 0) return FFB_OK;
+  if (!vec_dev) return fail(FFB_EINVAL, "ffb_apply_num_op_prod_phase: NULL state");
+  int rc;
+  if ((rc = ensure_device_strings(tables_a)) != FFB_OK) return rc;
+  if ((rc = ensure_device_strings(tables_b)) != FFB_OK) return rc;
+  DeviceInfo di;
+  if ((rc = get_device_info(&di)) != FFB_OK) return rc;
+  ProfScope prof(kProfOther, 0.0, (cudaStream_t)stream);
+  FFB_CUDA(launch_num_op_prod_phase(tables_a->d_strings, tables_b->d_strings, mask_a, mask_b, phase.re, phase.im,
+                                    vec_dev, row0, n_rows, col0, n_cols, ld, di.sm_count, (cudaStream_t)stream));
   return FFB_OK;
 }
 

@@ -10,6 +10,9 @@
 
 namespace ffb {
 
+#ifndef FFB_TPB
+#define FFB_TPB 512  // CTA size the fused kernel is compiled for (registers per thread = 64K / FFB_TPB)
+#endif
 constexpr int kMaxGroups = 33;       // distinct electron counts inside a window
 constexpr int kMaxRotPerPass = 512;  // >= 32*31/2
 constexpr int kMaxSubPerPass = 96;

@@ -294,6 +294,25 @@ __global__ void __launch_bounds__(1024) fp64_peak_kernel(double *out, double a, 
   if (s == 12345.678) out[0] = s;
 }
 
+// vec[a, b] *= phase where string a contains every orbital of mask_a and string b every orbital of
+// mask_b: the controlled phase behind the number-number, on-site and number-operator-product gates
+// (python/ffsim/gates/basic_gates.py:27-51).  One CTA per matching row; only matching amplitudes move.
+__global__ void num_op_prod_phase_kernel(const uint32_t *__restrict__ strings_a,
+                                         const uint32_t *__restrict__ strings_b, uint32_t mask_a,
+                                         uint32_t mask_b, double pr, double pi, double2 *__restrict__ vec,
+                                         long long row0, long long n_rows, long long col0, long long n_cols,
+                                         long long ld) {
+  for (long long r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    if ((strings_a[row0 + r] & mask_a) != mask_a) continue;
+    double2 *__restrict__ row = vec + r * ld;
+    for (long long c = threadIdx.x; c < n_cols; c += blockDim.x) {
+      if ((strings_b[col0 + c] & mask_b) != mask_b) continue;
+      const double2 x = row[c];
+      row[c] = make_double2(x.x * pr - x.y * pi, x.x * pi + x.y * pr);
+    }
+  }
+}
+
 int grid_1d(long long total, int threads, int sm_count, int per_sm) {
   long long blocks = (total + threads - 1) / threads;
   long long cap = (long long)sm_count * per_sm;
@@ -363,6 +382,17 @@ cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t
   if (contract) return rpw == 2 ? launch(diag_kernel<Re, true, 2, 2>) : launch(diag_kernel<Re, true, 1, 4>);
   if (rpw == 2) return one_wave ? launch(diag_kernel<Cx, false, 2, 4>) : launch(diag_kernel<Cx, false, 2, 2>);
   return launch(diag_kernel<Cx, false, 1, 4>);
+}
+
+cudaError_t launch_num_op_prod_phase(const uint32_t *strings_a, const uint32_t *strings_b, uint32_t mask_a,
+                                     uint32_t mask_b, double pr, double pi, void *vec, long long row0,
+                                     long long n_rows, long long col0, long long n_cols, long long ld,
+                                     int sm_count, cudaStream_t stream) {
+  if (n_rows <= 0 || n_cols <= 0) return cudaSuccess;
+  const long long grid = std::min<long long>(n_rows, (long long)sm_count * 16);
+  num_op_prod_phase_kernel<<<(int)grid, 256, 0, stream>>>(strings_a, strings_b, mask_a, mask_b, pr, pi,
+                                                          (double2 *)vec, row0, n_rows, col0, n_cols, ld);
+  return cudaGetLastError();
 }
 
 cudaError_t measure_fp64_peak(int sm_count, double *tflops) {

@@ -310,10 +310,9 @@ __device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const ui
   return w;
 }
 
-#ifndef FFB_TPB
-#define FFB_TPB 512  // CTA size the fused kernel is compiled for (registers per thread = 64K / FFB_TPB)
-#endif
+// FFB_TPB (device_structs.h): the CTA size the kernel is compiled for; smaller CTAs may be launched
 constexpr int kTilePerThread = (14336 + FFB_TPB - 1) / FFB_TPB;  // >= 220 KB / 16 B / CTA size (28 at 512 threads)
+static_assert(kTilePerThread % 2 == 0, "the tile store walks a thread's elements in two halves");
 
 template <int W>
 __global__ void __launch_bounds__(FFB_TPB, 1)

@@ -56,6 +56,10 @@ cudaError_t launch_diag(bool contract, const uint32_t *strings_a, const uint32_t
                         void *out, long long row0, long long n_rows, long long col0, long long n_cols,
                         long long ld, int norb, int zrep, int accumulate, int sm_count,
                         cudaStream_t stream);
+cudaError_t launch_num_op_prod_phase(const uint32_t *strings_a, const uint32_t *strings_b, uint32_t mask_a,
+                                     uint32_t mask_b, double pr, double pi, void *vec, long long row0,
+                                     long long n_rows, long long col0, long long n_cols, long long ld,
+                                     int sm_count, cudaStream_t stream);
 // Roofline denominator of the fused Givens kernel: dense DFMA throughput of this device (TFLOP/s,
 // 2 flops per DFMA), best of a few launches of an unrolled independent-chain kernel.
 cudaError_t measure_fp64_peak(int sm_count, double *tflops);

@@ -9,7 +9,7 @@
 // There is no counterpart in the reference: it performs one sweep per rotation
 // (python/ffsim/gates/orbital_rotation.py:132-135).
 #include <algorithm>
-#include <cassert>
+#include <stdexcept>
 #include <cstdlib>
 #include <cstring>
 
@@ -35,9 +35,19 @@ int class_offset(int w, int mprime) {
   return off;
 }
 
+// Invariants of the plan tables: violated only by a bug in the builder, never by user input.  They
+// surface as FFB_EINTERNAL through the C ABI (capi.cu catches), not as an abort of the host process.
+static void require(bool ok, const char *what) {
+  if (!ok) throw std::logic_error(std::string("plan builder invariant violated: ") + what);
+}
+
 int max_window(int norb, int nocc, const PlanOptions &opt) {
   int64_t budget_amps = opt.smem_bytes / 16;
-  for (int W = norb; W >= 2; --W) {
+  // a register block starts at most W - w orbitals into the window, and the block-offset tables hold
+  // kMaxLow distinct counts of electrons below it: cap the window accordingly (nearly-filled sectors of
+  // norb >= 22 would otherwise reach counts >= kMaxLow)
+  const int w_reg = std::max(2, std::min(opt.sub_window, kMaxSubWindow));
+  for (int W = std::min(norb, kMaxLow - 1 + w_reg); W >= 2; --W) {
     int mlo = std::max(0, nocc - (norb - W)), mhi = std::min(W, nocc);
     uint64_t maxR = 0;
     for (int m = mlo; m <= mhi; ++m) maxR = std::max(maxR, binom(W, m));
@@ -116,7 +126,7 @@ static std::vector<Group> tile_sequence(const std::vector<int> &index, const std
         next.push_back(std::move(ns));
       }
     }
-    assert(!next.empty());
+    require(!next.empty(), "no window admits a rotation");
     // finished states win; otherwise keep the states with the fewest rotations left
     std::stable_sort(next.begin(), next.end(), [](const State &a, const State &b) {
       return a.remaining.size() < b.remaining.size();
@@ -166,7 +176,7 @@ static SideSchedule build_schedule_for(int norb, int nocc, const std::vector<int
     // level 1: sweeps over the state.  (Re-planned from the rotations still left, so a pass
     // that had to hand rotations back -- see below -- is followed by a consistent schedule.)
     std::vector<Group> passes = tile_sequence(remaining, q, norb, W, kMaxRotPerPass, 1u << 30);
-    assert(!passes.empty());
+    require(!passes.empty(), "empty pass list");
     bool handed_back = false;
     for (const Group &pg : passes) {
       PassSchedule pass;
@@ -294,12 +304,12 @@ PassTablesHost build_pass_tables(int norb, int nocc, const PassSchedule &pass) {
         for (uint64_t Hp = 0; Hp < n_up; ++Hp) {
           int lp = m - __builtin_popcountll(Hp) - mp;
           if (lp < 0 || lp > sp.q0) continue;
-          assert(lp < kMaxLow);
+          require(lp < kMaxLow, "electron count below the register block exceeds the offset table");
           uint64_t hb = placed_rank(Hp, sp.q0 + sp.w, lp + mp + 1);
           uint64_t nL = binom(sp.q0, lp);
           for (uint64_t r = 0; r < nL; ++r) {
             uint64_t base = hb + r;
-            assert(base < (1u << 24));
+            require(base < (1u << 24), "block base row exceeds 24 bits");
             gs.blocks.push_back((uint32_t)base | ((uint32_t)lp << 24));
           }
         }
@@ -326,7 +336,7 @@ PassTablesHost build_pass_tables(int norb, int nocc, const PassSchedule &pass) {
               res = (res + 1) & 7;
             }
           }
-          assert(pos == gs.blocks.size());
+          require(pos == gs.blocks.size(), "block reordering lost entries");
         }
         if (count > 0) {
           gs.seg_mp[gs.n_seg] = mp;
@@ -421,7 +431,8 @@ int ffb_set_option(const char *key, int64_t value) {
     if (value < 2 || value > kMaxSubWindow) return fail(FFB_EINVAL, "sub_window out of range");
     g_opt.sub_window = (int)value;
   } else if (k == "threads") {
-    if (value < 32 || value > 1024 || value % 32) return fail(FFB_EINVAL, "threads out of range");
+    if (value < 32 || value > FFB_TPB || value % 32)
+      return fail(FFB_EINVAL, "threads out of range (32.." + std::to_string(FFB_TPB) + ", the CTA size the kernel is built for)");
     g_opt.threads = (int)value;
   } else if (k == "beta_mode") {
     if (value < 0 || value > 2) return fail(FFB_EINVAL, "beta_mode out of range");

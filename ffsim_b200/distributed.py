@@ -342,7 +342,7 @@ class _SymmBuffer:
 
 
 _SYMM_POOL: dict[tuple, list[_SymmBuffer]] = {}
-_SYMM_STATE = {"checked": False, "ok": False}
+_SYMM_STATE = {"checked": False, "ok": False, "sync": None}
 
 
 def _symm_get(numel: int, device, group) -> _SymmBuffer:
@@ -377,6 +377,10 @@ def p2p_available(sv: "ShardedVector") -> bool:
         try:
             probe = _SymmBuffer(16, sv.device, sv.group)
             ok = int(len(probe.ptrs) == sv.world and all(probe.ptrs))
+            # every cross-rank barrier of the exchange goes through THIS handle: symmetric allocations that
+            # share a memory-pool block share a signal pad, and a barrier keeps per-handle state, so
+            # alternating barriers on the handles of (small, pooled) data buffers can deadlock
+            _SYMM_STATE["sync"] = probe
         except Exception:
             ok = 0
         flag = torch.tensor([ok], device=sv.device, dtype=torch.int32)
@@ -395,9 +399,8 @@ def _symm_numel(sv: ShardedVector) -> int:
 
 def _make_symmetric(sv: ShardedVector) -> _SymmBuffer:
     """Move the shard into symmetric memory (once per vector; it stays there)."""
-    buf = sv._symm
-    if buf is not None and sv.local is not None and sv.local.data_ptr() == buf.tensor.data_ptr():
-        return buf
+    if sv._symm is not None:  # set by _adopt exactly when ``local`` is a view of that buffer (an EMPTY view has
+        return sv._symm       # no data pointer to compare: ranks with a zero-size shard must take this path too)
     buf = _symm_get(_symm_numel(sv), sv.device, sv.group)
     view = buf.tensor[: sv.local.numel()]
     view.copy_(sv.local)
@@ -409,15 +412,16 @@ def _redistribute_p2p(sv: ShardedVector, layout: str) -> None:
     """One kernel: every rank stores its blocks straight into their final place in the peers' shards."""
     src_buf = _make_symmetric(sv)
     dst_buf = _symm_get(_symm_numel(sv), sv.device, sv.group)
+    sync = _SYMM_STATE["sync"].handle
     with torch.cuda.device(sv.device):
-        dst_buf.handle.barrier(channel=0)  # peers may still be reading this buffer from an earlier exchange
+        sync.barrier(channel=0)  # peers may still be reading this buffer from an earlier exchange
         if layout == COLS:
             g = _row_block_geometry(sv)
             _copy_blocks(sv.local, sv.dim_b, g["rows"], g["width"], g["row_off"], dst_buf.ptrs, g["col_off"], g["col_ld"])
         else:
             g = _col_block_geometry(sv)
             _copy_blocks(sv.local, sv.n_cols, g["rows"], g["width"], g["col_off"], dst_buf.ptrs, g["row_off"], g["row_ld"])
-        dst_buf.handle.barrier(channel=0)
+        sync.barrier(channel=0)  # every block has landed before anyone reads its new shard
     del src_buf  # _adopt hands the old buffer back to the pool
     sv._adopt(dst_buf.tensor[: sv.local_numel(layout)], layout, dst_buf)
 

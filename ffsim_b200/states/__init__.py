@@ -41,4 +41,6 @@ def hartree_fock_state(norb: int, nelec: int | tuple[int, int], *, device: Any =
     return vec
 
 
-__all__ = ["dim", "dims", "hartree_fock_state"]
+from ffsim_b200.states.spin import Spin, pair_for_spin  # noqa: E402
+
+__all__ = ["Spin", "dim", "dims", "hartree_fock_state", "pair_for_spin"]

@@ -4,9 +4,8 @@ python/ffsim/trotter/qdrift.py:23-241 (driver), :244-348 (sampling probabilities
 
 Every sampled term is one rotated number-operator-sum or diagonal-Coulomb evolution on the
 device; consecutive basis changes are merged into a single orbital rotation, as in
-``simulate_trotter_double_factorized``.  The state-dependent "optimal" probabilities need the
-Wick-expectation machinery of python/ffsim/states/wick.py, which is outside the hot path: pass an
-explicit probability array instead.
+``simulate_trotter_double_factorized``.  The state-dependent "optimal" / "optimal-incoherent"
+probabilities (qdrift.py:304-343) use the Wick expectation values of ``ffsim_b200/states/wick.py`` (host).
 """
 
 from __future__ import annotations
@@ -23,6 +22,7 @@ from ffsim_b200.gates.diag_coulomb import _evolve_device, _get_mat_exp
 from ffsim_b200.gates.num_op_sum import _evolve_device as _evolve_num_op_sum
 from ffsim_b200.gates.orbital_rotation import _check_dim, _rotate_device
 from ffsim_b200.hamiltonians.double_factorized_hamiltonian import DoubleFactorizedHamiltonian
+from ffsim_b200.states.wick import expectation_one_body_power, expectation_one_body_product
 
 
 def spectral_norm_one_body_tensor(one_body_tensor, *, nelec, z_representation: bool = False) -> float:
@@ -84,11 +84,74 @@ def qdrift_probabilities(hamiltonian: DoubleFactorizedHamiltonian, sampling_meth
     if sampling_method in ("optimal", "optimal-incoherent"):
         if one_rdm is None:
             raise ValueError(f"The '{sampling_method}' sampling method requires one_rdm to be specified.")
-        raise NotImplementedError(
-            f"sampling method '{sampling_method}' needs the Wick expectation values of ffsim.states.wick, "
-            "which are outside this package; pass the probabilities as an array"
-        )
+        one_body = scipy.linalg.block_diag(hamiltonian.one_body_tensor, hamiltonian.one_body_tensor)
+        incoherent = sampling_method == "optimal-incoherent"
+        weights = np.zeros(n_terms)
+        weights[0] = (expectation_one_body_power(one_rdm, one_body, 2).real if incoherent
+                      else variance_one_body_tensor(one_rdm, one_body))
+        for i, mat in enumerate(hamiltonian.diag_coulomb_mats):
+            moments = _diag_coulomb_moments(one_rdm, mat, hamiltonian.orbital_rotations[i],
+                                            hamiltonian.z_representation)
+            weights[i + 1] = moments[1].real if incoherent else max(0, (moments[1] - abs(moments[0]) ** 2).real)
+        stds = np.sqrt(weights)
+        return stds / np.sum(stds)
     raise ValueError(f"Unsupported sampling method: {sampling_method}.")
+
+
+def one_body_square_decomposition(diag_coulomb_mat: np.ndarray, orbital_rotation: np.ndarray | None = None,
+                                  truncation_threshold: float = 1e-12) -> np.ndarray:
+    """One-body matrices whose squares sum to the two-body term: sqrt(lambda_t / 2) U diag(v_t) U^dagger
+    for every eigenpair of the diagonal Coulomb matrix (qdrift.py:432-460)."""
+    if orbital_rotation is None:
+        orbital_rotation = np.eye(diag_coulomb_mat.shape[0])
+    eigs, vecs = scipy.linalg.eigh(diag_coulomb_mat)
+    keep = np.abs(eigs) >= truncation_threshold
+    eigs, vecs = eigs[keep], vecs[:, keep]
+    scale = np.emath.sqrt(0.5 * eigs)
+    return np.stack([scale[t] * (orbital_rotation * vecs[:, t]) @ orbital_rotation.T.conj() for t in range(len(eigs))]) \
+        if len(eigs) else np.zeros((0,) + diag_coulomb_mat.shape, dtype=complex)
+
+
+def variance_one_body_tensor(one_rdm: np.ndarray, one_body_tensor: np.ndarray) -> float:
+    """Variance of a one-body operator in a Slater determinant (qdrift.py:463-480)."""
+    var = (expectation_one_body_power(one_rdm, one_body_tensor, 2)
+           - abs(expectation_one_body_power(one_rdm, one_body_tensor, 1)) ** 2).real
+    return max(0, var)
+
+
+def _diag_coulomb_moments(one_rdm, diag_coulomb_mat, orbital_rotation, z_representation):
+    """(<T>, <T^2>) of a rotated diagonal Coulomb term T = sum_t O_t^2 in a Slater determinant
+    (qdrift.py:483-613).  In the Z representation the term carries a one-body correction; the reference
+    adds its cross terms with the LAST square root only (``one_body_op`` is the loop variable of the
+    preceding loop there) -- kept, since these numbers only steer sampling probabilities and must agree."""
+    if orbital_rotation is None:
+        orbital_rotation = np.eye(diag_coulomb_mat.shape[0])
+    ops = [scipy.linalg.block_diag(m, m) for m in one_body_square_decomposition(diag_coulomb_mat, orbital_rotation)]
+    first = sum((expectation_one_body_power(one_rdm, op, 2) for op in ops), 0j)
+    second = sum((expectation_one_body_power(one_rdm, op, 4) for op in ops), 0j)
+    for op1, op2 in itertools.combinations(ops, 2):
+        second += 2 * expectation_one_body_product(one_rdm, [op1, op1, op2, op2])
+    if z_representation:
+        rot, rot_c = orbital_rotation, orbital_rotation.conj()
+        corr = -0.5 * (np.einsum("ij,pi,qi->pq", diag_coulomb_mat, rot, rot_c)
+                       + np.einsum("ij,pj,qj->pq", diag_coulomb_mat, rot, rot_c))
+        corr = scipy.linalg.block_diag(corr, corr)
+        first += expectation_one_body_power(one_rdm, corr, 1)
+        second += expectation_one_body_power(one_rdm, corr, 2)
+        if ops:
+            second += expectation_one_body_product(one_rdm, [corr, ops[-1], ops[-1]])
+            second += expectation_one_body_product(one_rdm, [ops[-1], ops[-1], corr])
+    return first, second
+
+
+def variance_diag_coulomb(one_rdm, diag_coulomb_mat, orbital_rotation=None, z_representation: bool = False) -> float:
+    first, second = _diag_coulomb_moments(one_rdm, diag_coulomb_mat, orbital_rotation, z_representation)
+    return max(0, (second - abs(first) ** 2).real)
+
+
+def expectation_squared_diag_coulomb(one_rdm, diag_coulomb_mat, orbital_rotation=None,
+                                     z_representation: bool = False) -> float:
+    return _diag_coulomb_moments(one_rdm, diag_coulomb_mat, orbital_rotation, z_representation)[1].real
 
 
 def simulate_qdrift_double_factorized(

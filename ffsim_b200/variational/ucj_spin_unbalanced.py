@@ -15,6 +15,7 @@ from dataclasses import InitVar, dataclass
 import numpy as np
 
 from ffsim_b200 import _device, linalg
+from ffsim_b200.variational import _packing
 from ffsim_b200.gates.diag_coulomb import _evolve_device, _get_mat_exp
 from ffsim_b200.gates.orbital_rotation import _check_dim, _rotate_device
 
@@ -76,6 +77,23 @@ class UCJOpSpinUnbalanced:
     @property
     def n_reps(self) -> int:
         return self.diag_coulomb_mats.shape[0]
+
+    @staticmethod
+    def n_params(norb: int, n_reps: int, *, interaction_pairs=None, with_final_orbital_rotation: bool = False) -> int:
+        """Number of real parameters (interaction_pairs = (alpha-alpha, alpha-beta, beta-beta); the alpha-beta pairs are ordered)."""
+        return _packing.count(norb, n_reps, (_packing.SYM, _packing.FULL, _packing.SYM), interaction_pairs, 2, with_final_orbital_rotation)
+
+    @staticmethod
+    def from_parameters(params: np.ndarray, *, norb: int, n_reps: int, interaction_pairs=None,
+                        with_final_orbital_rotation: bool = False) -> "UCJOpSpinUnbalanced":
+        """Build the operator from a real parameter vector (the reference's layout, see ``_packing``)."""
+        mats, rots, final = _packing.unpack(params, norb, n_reps, (_packing.SYM, _packing.FULL, _packing.SYM), interaction_pairs, 2,
+                                            with_final_orbital_rotation)
+        return UCJOpSpinUnbalanced(diag_coulomb_mats=mats, orbital_rotations=rots, final_orbital_rotation=final)
+
+    def to_parameters(self, *, interaction_pairs=None) -> np.ndarray:
+        """The inverse of ``from_parameters`` (entries outside ``interaction_pairs`` are dropped)."""
+        return _packing.pack(self.diag_coulomb_mats, self.orbital_rotations, self.final_orbital_rotation, (_packing.SYM, _packing.FULL, _packing.SYM), interaction_pairs)
 
     def _apply_unitary_(self, vec, norb: int, nelec, copy: bool):
         if isinstance(nelec, numbers.Integral):

@@ -14,6 +14,7 @@ from dataclasses import InitVar, dataclass
 import numpy as np
 
 from ffsim_b200 import _device, linalg
+from ffsim_b200.variational import _packing
 from ffsim_b200.gates.diag_coulomb import _evolve_device, _get_mat_exp
 from ffsim_b200.gates.orbital_rotation import _check_dim, _rotate_device
 
@@ -68,6 +69,27 @@ class UCJOpSpinless:
     @property
     def n_reps(self) -> int:
         return self.diag_coulomb_mats.shape[0]
+
+    @staticmethod
+    def n_params(norb: int, n_reps: int, *, interaction_pairs=None, with_final_orbital_rotation: bool = False) -> int:
+        """Number of real parameters (interaction_pairs = a list of upper triangular pairs; None = all)."""
+        return _packing.count(norb, n_reps, (_packing.SYM,), None if interaction_pairs is None else (interaction_pairs,), 1,
+                              with_final_orbital_rotation)
+
+    @staticmethod
+    def from_parameters(params: np.ndarray, *, norb: int, n_reps: int, interaction_pairs=None,
+                        with_final_orbital_rotation: bool = False) -> "UCJOpSpinless":
+        """Build the operator from a real parameter vector (the reference's layout, see ``_packing``)."""
+        mats, rots, final = _packing.unpack(params, norb, n_reps, (_packing.SYM,),
+                                            None if interaction_pairs is None else (interaction_pairs,), 1,
+                                            with_final_orbital_rotation)
+        return UCJOpSpinless(diag_coulomb_mats=mats[:, 0], orbital_rotations=rots[:, 0],
+                             final_orbital_rotation=None if final is None else final[0])
+
+    def to_parameters(self, *, interaction_pairs=None) -> np.ndarray:
+        """The inverse of ``from_parameters`` (entries outside ``interaction_pairs`` are dropped)."""
+        return _packing.pack(self.diag_coulomb_mats[:, None], self.orbital_rotations[:, None], None if self.final_orbital_rotation is None else self.final_orbital_rotation[None], (_packing.SYM,),
+                             None if interaction_pairs is None else (interaction_pairs,))
 
     def _apply_unitary_(self, vec, norb: int, nelec, copy: bool):
         spinless = isinstance(nelec, numbers.Integral)

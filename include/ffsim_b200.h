@@ -204,6 +204,14 @@ int ffb_contract_num_op_sum_block(ffb_tables *tables_a, ffb_tables *tables_b, co
                                   int accumulate, int64_t row0, int64_t n_rows, int64_t col0,
                                   int64_t n_cols, int64_t ld, void *stream);
 
+/* vec[a,b] *= phase wherever string a contains every orbital of mask_a and string b every orbital of
+ * mask_b (bit i = orbital i): the controlled phase shift of python/ffsim/gates/basic_gates.py:27-51
+ * behind apply_num_num_interaction, apply_on_site_interaction and apply_num_op_prod_interaction.
+ * Block arguments as in the _block calls above (n_cols < 0: whole beta sector). */
+int ffb_apply_num_op_prod_phase(ffb_tables *tables_a, ffb_tables *tables_b, uint32_t mask_a, uint32_t mask_b,
+                                ffb_c128 phase, void *vec_dev, int64_t row0, int64_t n_rows, int64_t col0,
+                                int64_t n_cols, int64_t ld, void *stream);
+
 /* ---------------------------------------------------------------- utilities */
 /* out[c, r] = in[r, c]; in is n_rows x n_cols with row stride ld_in, out has row stride ld_out. */
 int ffb_transpose(const void *in_dev, void *out_dev, int64_t n_rows, int64_t n_cols, int64_t ld_in,

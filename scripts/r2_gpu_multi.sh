@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2 multi-GPU check: sharded tests + the contract bench at N ranks, both exchange implementations
+N=${1:-2}; TAG=${2:-r2j}
+mkdir -p gpurun_out
+nvidia-smi -L > gpurun_out/${TAG}_gpus.txt
+timeout 900 python -m pytest tests/test_gpu_distributed.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
+for mode in nccl p2p; do
+  FFSIM_B200_EXCHANGE=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
+    bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_${mode}.json 2> gpurun_out/${TAG}_bench_${mode}.err; echo "rc=$?" >> gpurun_out/${TAG}_bench_${mode}.err
+done
+tail -3 gpurun_out/${TAG}_pytest.log

@@ -21,6 +21,10 @@ from oracle import cref, models, rand
 
 
 def main():
+    if os.environ.get("FFSIM_B200_WATCHDOG"):  # a hung collective prints every thread's stack and exits
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["FFSIM_B200_WATCHDOG"]), exit=True)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)

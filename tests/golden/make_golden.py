@@ -276,6 +276,117 @@ def main():
             mean=kw.get("diag_coulomb_mean", 0.0), diag_coulomb_mats=op.diag_coulomb_mats,
             orbital_rotations=op.orbital_rotations, final_orbital_rotation=opt(op.final_orbital_rotation))
 
+    # ---- round 2: the rest of SURVEY.md section 8f (appended; earlier random streams unchanged) ----
+    from ffsim.gates import basic_gates as bg
+    from ffsim.states.spin import Spin
+    from ffsim.trotter.qdrift import qdrift_probabilities
+    from ffsim.variational.givens import GivensAnsatzOp
+    from ffsim.variational.ucj_angles_spin_balanced import UCJAnglesOpSpinBalanced
+    from ffsim.variational.ucj_spin_balanced import UCJOpSpinBalanced
+    from ffsim.variational.ucj_spin_unbalanced import UCJOpSpinUnbalanced
+    from ffsim.variational.ucj_spinless import UCJOpSpinless
+
+    rng2 = np.random.default_rng(20261018)
+    spins = {"a": Spin.ALPHA, "b": Spin.BETA, "ab": Spin.ALPHA_AND_BETA}
+    # named gates (gates/basic_gates.py:54-629): spinful with every spin choice, and spinless
+    for norb, nelec in [(4, (2, 2)), (5, (3, 2)), (5, 2)]:
+        vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng2)
+        tag = f"{norb}_{nelec}" if isinstance(nelec, int) else f"{norb}_{nelec[0]}_{nelec[1]}"
+        theta, phi = 0.37, -0.81
+        for sname, spin in spins.items():
+            if isinstance(nelec, int) and sname != "ab":
+                continue
+            kw = dict(norb=norb, nelec=nelec, spin=spin)
+            meta = dict(norb=norb, nelec=nelec, vec=vec, theta=theta, phi=phi, spin=np.array(list(sname.encode())))
+            add(f"basic/givens_{tag}_{sname}", kind="basic", gate=np.array(list(b"givens")), orbs=(1, 3), **meta,
+                expected=bg.apply_givens_rotation(vec, theta, (1, 3), phi=phi, **kw))
+            add(f"basic/tunneling_{tag}_{sname}", kind="basic", gate=np.array(list(b"tunneling")), orbs=(0, 2), **meta,
+                expected=bg.apply_tunneling_interaction(vec, theta, (0, 2), **kw))
+            add(f"basic/num_{tag}_{sname}", kind="basic", gate=np.array(list(b"num")), orbs=(2, 2), **meta,
+                expected=bg.apply_num_interaction(vec, theta, 2, **kw))
+            add(f"basic/num_num_{tag}_{sname}", kind="basic", gate=np.array(list(b"num_num")), orbs=(1, 2), **meta,
+                expected=bg.apply_num_num_interaction(vec, theta, (1, 2), **kw))
+            add(f"basic/hop_{tag}_{sname}", kind="basic", gate=np.array(list(b"hop")), orbs=(3, 1), **meta,
+                expected=bg.apply_hop_gate(vec, theta, (3, 1), **kw))
+            add(f"basic/fsim_{tag}_{sname}", kind="basic", gate=np.array(list(b"fsim")), orbs=(0, 1), **meta,
+                expected=bg.apply_fsim_gate(vec, theta, phi, (0, 1), **kw))
+            add(f"basic/fswap_{tag}_{sname}", kind="basic", gate=np.array(list(b"fswap")), orbs=(2, 3), **meta,
+                expected=bg.apply_fswap_gate(vec, (2, 3), **kw))
+        if not isinstance(nelec, int):
+            add(f"basic/on_site_{tag}", kind="basic", gate=np.array(list(b"on_site")), orbs=(1, 1), norb=norb,
+                nelec=nelec, vec=vec, theta=theta, phi=phi, spin=np.array(list(b"ab")),
+                expected=bg.apply_on_site_interaction(vec, theta, 1, norb=norb, nelec=nelec))
+            add(f"basic/num_op_prod_{tag}", kind="basic", gate=np.array(list(b"num_op_prod")), orbs=(0, 2), norb=norb,
+                nelec=nelec, vec=vec, theta=theta, phi=phi, spin=np.array(list(b"ab")),
+                expected=bg.apply_num_op_prod_interaction(vec, theta, ([0, 2], [1]), norb=norb, nelec=nelec))
+
+    # parameter vectors of the UCJ operators (ucj_spin_balanced.py:144-295 and siblings)
+    op = rr.random_ucj_op_spin_balanced(4, n_reps=2, with_final_orbital_rotation=True, seed=6101)
+    pairs = ([(0, 1), (1, 2), (2, 3)], [(0, 0), (1, 1), (2, 2), (3, 3)])
+    add("params/ucj_balanced_full", kind="params_balanced", norb=4, n_reps=2, final=1, pairs_aa=NONE, pairs_ab=NONE,
+        diag_coulomb_mats=op.diag_coulomb_mats, orbital_rotations=op.orbital_rotations,
+        final_orbital_rotation=op.final_orbital_rotation, expected=op.to_parameters())
+    add("params/ucj_balanced_pairs", kind="params_balanced", norb=4, n_reps=2, final=1, pairs_aa=np.array(pairs[0]),
+        pairs_ab=np.array(pairs[1]), diag_coulomb_mats=op.diag_coulomb_mats, orbital_rotations=op.orbital_rotations,
+        final_orbital_rotation=op.final_orbital_rotation, expected=op.to_parameters(interaction_pairs=pairs))
+    params = rng2.uniform(-1, 1, UCJOpSpinBalanced.n_params(4, 2, interaction_pairs=pairs, with_final_orbital_rotation=True))
+    op2 = UCJOpSpinBalanced.from_parameters(params, norb=4, n_reps=2, interaction_pairs=pairs,
+                                            with_final_orbital_rotation=True)
+    add("params/ucj_balanced_from", kind="params_balanced_from", norb=4, n_reps=2, final=1, pairs_aa=np.array(pairs[0]),
+        pairs_ab=np.array(pairs[1]), params=params, diag_coulomb_mats=op2.diag_coulomb_mats,
+        orbital_rotations=op2.orbital_rotations, final_orbital_rotation=op2.final_orbital_rotation)
+    opu = rr.random_ucj_op_spin_unbalanced(3, n_reps=2, with_final_orbital_rotation=True, seed=6102)
+    add("params/ucj_unbalanced_full", kind="params_unbalanced", norb=3, n_reps=2, final=1,
+        diag_coulomb_mats=opu.diag_coulomb_mats, orbital_rotations=opu.orbital_rotations,
+        final_orbital_rotation=opu.final_orbital_rotation, expected=opu.to_parameters(),
+        n_params=UCJOpSpinUnbalanced.n_params(3, 2, with_final_orbital_rotation=True))
+    ops = rr.random_ucj_op_spinless(4, n_reps=2, with_final_orbital_rotation=False, seed=6103)
+    add("params/ucj_spinless_pairs", kind="params_spinless", norb=4, n_reps=2, final=0, pairs=np.array([(0, 1), (1, 3)]),
+        diag_coulomb_mats=ops.diag_coulomb_mats, orbital_rotations=ops.orbital_rotations,
+        expected=ops.to_parameters(interaction_pairs=[(0, 1), (1, 3)]),
+        n_params=UCJOpSpinless.n_params(4, 2, interaction_pairs=[(0, 1), (1, 3)]))
+
+    # GivensAnsatzOp / UCJAnglesOpSpinBalanced (variational/givens.py, ucj_angles_spin_balanced.py)
+    u = rr.random_unitary(5, seed=6104)
+    g = GivensAnsatzOp.from_orbital_rotation(u)
+    add("angles/givens_from_rotation_5", kind="givens_from_rotation", norb=5, mat=u,
+        pairs=np.array(g.interaction_pairs), thetas=g.thetas, phis=g.phis, phase_angles=g.phase_angles,
+        rotation=g.to_orbital_rotation())
+    for norb, nelec, n_reps, final in [(4, (2, 2), 2, True), (5, (2, 3), 1, False)]:
+        nn_pairs = ([(p, p + 1) for p in range(norb - 1)], [(p, p) for p in range(norb)])
+        g_pairs = [(p, p + 1) for p in range(0, norb - 1, 2)] + [(p, p + 1) for p in range(1, norb - 1, 2)]
+        n_par = UCJAnglesOpSpinBalanced.n_params(norb, n_reps, nn_pairs, g_pairs, with_final_givens_ansatz_op=final)
+        params = rng2.uniform(-np.pi, np.pi, n_par)
+        aop = UCJAnglesOpSpinBalanced.from_parameters(params, norb=norb, n_reps=n_reps, num_num_interaction_pairs=nn_pairs,
+                                                      givens_interaction_pairs=g_pairs, with_final_givens_ansatz_op=final)
+        vec = rr.random_state_vector(ref_dim(norb, nelec), seed=rng2)
+        add(f"angles/ucj_angles_{norb}_{nelec[0]}_{nelec[1]}_L{n_reps}", kind="ucj_angles", norb=norb, nelec=nelec,
+            n_reps=n_reps, final=int(final), params=params, pairs_aa=np.array(nn_pairs[0]), pairs_ab=np.array(nn_pairs[1]),
+            givens_pairs=np.array(g_pairs), vec=vec, roundtrip=aop.to_parameters(),
+            expected=apply_unitary(vec, aop, norb=norb, nelec=nelec))
+    ucj = rr.random_ucj_op_spin_balanced(4, n_reps=2, with_final_orbital_rotation=True, seed=6105)
+    aop = UCJAnglesOpSpinBalanced.from_ucj_op(ucj)
+    vec = rr.random_state_vector(ref_dim(4, (2, 2)), seed=rng2)
+    add("angles/from_ucj_op_4", kind="ucj_angles_from_ucj", norb=4, nelec=(2, 2), vec=vec,
+        diag_coulomb_mats=ucj.diag_coulomb_mats, orbital_rotations=ucj.orbital_rotations,
+        final_orbital_rotation=ucj.final_orbital_rotation, params=aop.to_parameters(),
+        expected=apply_unitary(vec, aop, norb=4, nelec=(2, 2)))
+
+    # qDRIFT sampling probabilities incl. the state-dependent ones (trotter/qdrift.py:247-348, states/wick.py)
+    for norb, nelec, rank, z in [(4, (2, 2), 3, False), (4, (1, 2), 2, True)]:
+        ham = rr.random_double_factorized_hamiltonian(norb, rank=rank, z_representation=z, seed=rng2)
+        # one-rdm of a Slater determinant (not spin-summed, spin-orbital basis): occupied orbitals of a random basis
+        import scipy.linalg
+        ua, ub = rr.random_unitary(norb, seed=rng2), rr.random_unitary(norb, seed=rng2)
+        rdm = scipy.linalg.block_diag((ua[:, : nelec[0]] @ ua[:, : nelec[0]].T.conj()).T,
+                                      (ub[:, : nelec[1]] @ ub[:, : nelec[1]].T.conj()).T)
+        tag = f"{norb}_{nelec[0]}_{nelec[1]}_r{rank}_{'z' if z else 'num'}"
+        for method in ("norm", "uniform", "optimal", "optimal-incoherent"):
+            add(f"qdrift_probs/{method}_{tag}", kind="qdrift_probs", norb=norb, nelec=nelec, z=z,
+                method=np.array(list(method.encode())), one_rdm=rdm, one_body_tensor=ham.one_body_tensor,
+                diag_coulomb_mats=ham.diag_coulomb_mats, orbital_rotations=ham.orbital_rotations, constant=ham.constant,
+                expected=qdrift_probabilities(ham, sampling_method=method, nelec=nelec, one_rdm=rdm))
+
     flat = {}
     for name, arrays in CASES.items():
         for k, v in arrays.items():

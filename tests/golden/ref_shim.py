@@ -98,6 +98,17 @@ def install():
     from oracle import cistring as ocis
     from oracle import givens as ogivens
 
+    # opt_einsum.contract is numpy.einsum with a different contraction-order optimiser
+    import numpy as _np
+    import opt_einsum as _oe  # (stub module)
+
+    _oe.contract = lambda subscripts, *operands, **kw: _np.einsum(subscripts, *operands, optimize=True)
+    # scipy's array-API helpers ask `issubclass(type(x), sys.modules["jax"].Array)` once "jax" is in
+    # sys.modules: give the stub a real (empty) class there
+    import jax as _jax  # (stub module)
+
+    _jax.Array = type("Array", (), {})
+
     # pyscf.fci.cistring
     import pyscf.fci  # noqa: F401  (stub)
 

@@ -7,6 +7,7 @@
 // suite validate the schedule and every index table without a GPU; it is not a
 // product path and nothing in ffsim_b200/ can reach it.
 #include <complex>
+#include <stdexcept>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -24,7 +25,7 @@ static void zrot(cplx &x, cplx &y, double c, cplx s) {
 extern "C" int ffb_hostcheck_apply_side(int norb, int nocc, const ffb_givens_rotation *rots, int n_rot,
                                         const ffb_c128 *phases, void *vec /* dim x n_cols, row-major */,
                                         int64_t n_cols, int64_t smem_bytes, int min_cols, int sub_window,
-                                        int *n_passes_out, int *n_subs_out) {
+                                        int *n_passes_out, int *n_subs_out) try {
   PlanOptions opt = current_options();
   if (smem_bytes > 0) opt.smem_bytes = smem_bytes;
   if (min_cols > 0) opt.min_cols = min_cols;
@@ -132,11 +133,13 @@ extern "C" int ffb_hostcheck_apply_side(int norb, int nocc, const ffb_givens_rot
   if (n_passes_out) *n_passes_out = (int)sched.passes.size();
   if (n_subs_out) *n_subs_out = total_subs;
   return 0;
+} catch (const std::exception &) {
+  return -200;  // a plan-builder invariant fired (plan.cpp require())
 }
 
 // Print the two-level schedule of a pair-position sequence (developer aid).
 extern "C" int ffb_hostcheck_dump_schedule(int norb, int nocc, const int *q, int n, int64_t smem_bytes,
-                                           int min_cols, int sub_window) {
+                                           int min_cols, int sub_window) try {
   PlanOptions opt = current_options();
   if (smem_bytes > 0) opt.smem_bytes = smem_bytes;
   if (min_cols > 0) opt.min_cols = min_cols;
@@ -153,6 +156,8 @@ extern "C" int ffb_hostcheck_dump_schedule(int norb, int nocc, const int *q, int
     }
   }
   return 0;
+} catch (const std::exception &) {
+  return -200;  // a plan-builder invariant fired (plan.cpp require())
 }
 
 // Shared-memory bank behaviour of the register-block gathers, from the block lists the kernel will
@@ -160,7 +165,7 @@ extern "C" int ffb_hostcheck_dump_schedule(int norb, int nocc, const int *q, int
 // access rows base + o[t]; rows that agree modulo 8 fall in the same 16-byte bank group.  Counts the
 // quarter-warps of every (pass, group, sub-pass, class) and the extra wavefronts their first access
 // needs (0 when the eight rows differ modulo 8).  out[0] = quarter-warps, out[1] = extra wavefronts.
-extern "C" int ffb_hostcheck_gather_conflicts(int norb, int nocc, const int *q, int n, int64_t *out) {
+extern "C" int ffb_hostcheck_gather_conflicts(int norb, int nocc, const int *q, int n, int64_t *out) try {
   PlanOptions opt = current_options();
   std::vector<int> qq(q, q + n);
   SideSchedule sched = build_schedule(norb, nocc, qq, opt);
@@ -192,6 +197,8 @@ extern "C" int ffb_hostcheck_gather_conflicts(int norb, int nocc, const int *q, 
   out[0] = quarters;
   out[1] = extra;
   return 0;
+} catch (const std::exception &) {
+  return -200;  // a plan-builder invariant fired (plan.cpp require())
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -208,7 +215,7 @@ static inline int fast_div_host(int n, uint32_t inv) { return inv ? (int)umulhi3
 extern "C" int ffb_hostcheck_apply_side_device(int norb, int nocc, const ffb_givens_rotation *rots, int n_rot,
                                                void *vec /* dim x n_cols, row-major */, int64_t n_cols,
                                                int64_t smem_bytes, int min_cols, int sub_window, int cols_req,
-                                               int nwarp) {
+                                               int nwarp) try {
   PlanOptions opt = current_options();
   if (smem_bytes > 0) opt.smem_bytes = smem_bytes;
   if (min_cols > 0) opt.min_cols = min_cols;
@@ -326,4 +333,6 @@ extern "C" int ffb_hostcheck_apply_side_device(int norb, int nocc, const ffb_giv
     }
   }
   return 0;
+} catch (const std::exception &) {
+  return -200;  // a plan-builder invariant fired (plan.cpp require())
 }

@@ -19,18 +19,22 @@ def test_sharded_world_size_1():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-def test_sharded_world_size_2(exchange):
+def test_sharded_world_size_n(exchange, world):
+    """The worker's checks (LUCJ, rotations, rotated diagonal Coulomb, DC-Hamiltonian energy, a Trotter step;
+    shapes with empty shards included) with the state distributed over 2, 4 and 8 ranks, both exchanges."""
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    env = dict(os.environ, FFSIM_B200_EXCHANGE=exchange, FFSIM_B200_REPORT_EXCHANGE="1")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, FFSIM_B200_EXCHANGE=exchange, FFSIM_B200_REPORT_EXCHANGE="1", FFSIM_B200_WATCHDOG="240")
+    port = 29700 + 2 * world + (exchange == "p2p")
     out = subprocess.run(
-        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-         "--master-addr", "127.0.0.1", "--master-port", "29711" if exchange == "p2p" else "29712", WORKER],
-        capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+         "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER],
+        capture_output=True, text=True, timeout=400, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
-    assert out.stdout.count("ok") == 2
+    assert out.stdout.count("ok") == world
     # the worker reports which path it actually took: no silent fallback
-    assert out.stdout.count(f"exchange={exchange}") == 2, out.stdout[-2000:]
+    assert out.stdout.count(f"exchange={exchange}") == world, out.stdout[-2000:]

@@ -151,6 +151,15 @@ def test_plan_tables_all_small_sectors(norb):
             assert err < 1e-13, (norb, k, smem, mc, sw, err)
 
 
+@pytest.mark.parametrize("norb,k", [(22, 19), (22, 20), (24, 22), (24, 23), (23, 20), (24, 2)])
+def test_plan_tables_nearly_filled_large_norb(norb, k):
+    """sectors of norb >= 22 with nocc >= norb - 3 used to reach more than kMaxLow
+    electrons below a register block (an assert, i.e. an abort of the host process).  The window is now
+    capped so that the offset tables always suffice; the emulated kernel must reproduce the oracle."""
+    err, n_pass, _ = _emulate(norb, k, 1, 220 * 1024, 3, 6, seed=norb + k)
+    assert err < 1e-12 and n_pass >= 1
+
+
 @pytest.mark.parametrize("norb,k,smem,max_passes", [
     (12, 6, 220 * 1024, 1), (12, 6, 16 * 1024, 4), (14, 5, 32 * 1024, 4), (16, 5, 220 * 1024, 1),
     (16, 8, 220 * 1024, 4)])

@@ -106,6 +106,51 @@ class OracleAPI:
             seed=int(c["seed"]))
 
 
+    def basic(self, vec, c, norb, nelec):
+        from oracle import basic_gates as bg
+
+        gate, spin = _text(c["gate"]), _text(c["spin"])
+        theta, phi, orbs = float(c["theta"]), float(c["phi"]), tuple(int(x) for x in c["orbs"])
+        if gate == "givens":
+            return bg.apply_givens_rotation(vec, theta, orbs, norb, nelec, spin, phi)
+        if gate == "tunneling":
+            return bg.apply_tunneling_interaction(vec, theta, orbs, norb, nelec, spin)
+        if gate == "num":
+            return bg.apply_num_interaction(vec, theta, orbs[0], norb, nelec, spin)
+        if gate == "num_num":
+            return bg.apply_num_num_interaction(vec, theta, orbs, norb, nelec, spin)
+        if gate == "hop":
+            return bg.apply_hop_gate(vec, theta, orbs, norb, nelec, spin)
+        if gate == "fsim":
+            return bg.apply_fsim_gate(vec, theta, phi, orbs, norb, nelec, spin)
+        if gate == "fswap":
+            return bg.apply_fswap_gate(vec, orbs, norb, nelec, spin)
+        if gate == "on_site":
+            return bg.apply_on_site_interaction(vec, theta, orbs[0], norb, nelec)
+        if gate == "num_op_prod":
+            return bg.apply_num_op_prod_interaction(vec, theta, ([0, 2], [1]), norb, nelec)
+        raise AssertionError(gate)
+
+    def ucj_angles(self, vec, c, norb, nelec):
+        from oracle import basic_gates as bg
+
+        return bg.ucj_angles_apply(vec, norb, nelec, int(c["n_reps"]), c["params"], _pairs(c["pairs_aa"]),
+                                   _pairs(c["pairs_ab"]), _pairs(c["givens_pairs"]), bool(c["final"]))
+
+    def ucj_angles_from_ucj(self, vec, c, norb, nelec):
+        # the angle form of a matrix-based operator applies the same unitary
+        return self.m.ucj_spin_balanced_apply(vec, c["diag_coulomb_mats"], c["orbital_rotations"],
+                                              opt(c["final_orbital_rotation"]), norb, nelec)
+
+
+def _text(a):
+    return bytes(np.asarray(a).astype(np.uint8)).decode()
+
+
+def _pairs(a):
+    return [tuple(int(x) for x in p) for p in np.asarray(a).reshape(-1, 2)]
+
+
 class CudaAPI:
     """ffsim_b200: the public drop-in API over the CUDA library."""
 
@@ -163,6 +208,53 @@ class CudaAPI:
             n_samples=int(c["n_samples"]), seed=int(c["seed"]))
 
 
+def _cuda_basic(f, vec, c, norb, nelec):
+    gate, sname = _text(c["gate"]), _text(c["spin"])
+    spin = {"a": f.Spin.ALPHA, "b": f.Spin.BETA, "ab": f.Spin.ALPHA_AND_BETA}[sname]
+    theta, phi, orbs = float(c["theta"]), float(c["phi"]), tuple(int(x) for x in c["orbs"])
+    kw = dict(norb=norb, nelec=nelec, spin=spin)
+    if gate == "givens":
+        return f.apply_givens_rotation(vec, theta, orbs, phi=phi, **kw)
+    if gate == "tunneling":
+        return f.apply_tunneling_interaction(vec, theta, orbs, **kw)
+    if gate == "num":
+        return f.apply_num_interaction(vec, theta, orbs[0], **kw)
+    if gate == "num_num":
+        return f.apply_num_num_interaction(vec, theta, orbs, **kw)
+    if gate == "hop":
+        return f.apply_hop_gate(vec, theta, orbs, **kw)
+    if gate == "fsim":
+        return f.apply_fsim_gate(vec, theta, phi, orbs, **kw)
+    if gate == "fswap":
+        return f.apply_fswap_gate(vec, orbs, **kw)
+    if gate == "on_site":
+        return f.apply_on_site_interaction(vec, theta, orbs[0], norb=norb, nelec=nelec)
+    if gate == "num_op_prod":
+        return f.apply_num_op_prod_interaction(vec, theta, ([0, 2], [1]), norb=norb, nelec=nelec)
+    raise AssertionError(gate)
+
+
+def _cuda_ucj_angles(f, vec, c, norb, nelec):
+    op = f.UCJAnglesOpSpinBalanced.from_parameters(
+        c["params"], norb=norb, n_reps=int(c["n_reps"]),
+        num_num_interaction_pairs=(_pairs(c["pairs_aa"]), _pairs(c["pairs_ab"])),
+        givens_interaction_pairs=_pairs(c["givens_pairs"]), with_final_givens_ansatz_op=bool(c["final"]))
+    assert np.array_equal(op.to_parameters(), c["roundtrip"])
+    return f.apply_unitary(vec, op, norb=norb, nelec=nelec)
+
+
+def _cuda_ucj_angles_from_ucj(f, vec, c, norb, nelec):
+    ucj = f.UCJOpSpinBalanced(c["diag_coulomb_mats"], c["orbital_rotations"], opt(c["final_orbital_rotation"]))
+    op = f.UCJAnglesOpSpinBalanced.from_ucj_op(ucj)
+    assert np.allclose(op.to_parameters(), c["params"], rtol=0, atol=1e-12)
+    return f.apply_unitary(vec, op, norb=norb, nelec=nelec)
+
+
+CudaAPI.basic = lambda self, vec, c, norb, nelec: _cuda_basic(self.f, vec, c, norb, nelec)
+CudaAPI.ucj_angles = lambda self, vec, c, norb, nelec: _cuda_ucj_angles(self.f, vec, c, norb, nelec)
+CudaAPI.ucj_angles_from_ucj = lambda self, vec, c, norb, nelec: _cuda_ucj_angles_from_ucj(self.f, vec, c, norb, nelec)
+
+
 def run_case(api, c):
     kind = str(c["kind"])
     norb, nelec, vec = int(c["norb"]), nelec_of(c), c["vec"]
@@ -196,7 +288,7 @@ def run_case(api, c):
         got = api.dc_matvec(vec, c, norb, nelec)
     elif kind == "dc_split_op":
         got = api.dc_split_op(vec, c, norb, nelec)
-    elif kind in ("ucj_unbalanced", "ucj_spinless", "df_matvec", "qdrift"):
+    elif kind in ("ucj_unbalanced", "ucj_spinless", "df_matvec", "qdrift", "basic", "ucj_angles", "ucj_angles_from_ucj"):
         got = getattr(api, kind)(vec, c, norb, nelec)
     else:
         raise AssertionError(kind)
@@ -204,7 +296,7 @@ def run_case(api, c):
     return got
 
 
-STATE_CASES = [n for n in CASES if not n.startswith(("random/", "random_op/", "tables/"))]
+STATE_CASES = [n for n in CASES if "vec" in CASES[n] and "expected" in CASES[n]]
 
 
 def test_fixture_is_complete():
@@ -212,8 +304,10 @@ def test_fixture_is_complete():
     assert kinds >= {"orbital_rotation", "orbital_rotation_spinless", "diag_coulomb", "diag_coulomb_spinless",
                      "num_op_sum", "contract_diag_coulomb", "contract_num_op_sum", "ucj", "trotter_df",
                      "dc_matvec", "dc_split_op", "zero_one", "one", "random_unitary",
-                     "ucj_unbalanced", "ucj_spinless", "df_matvec", "qdrift"}
-    assert len(STATE_CASES) >= 93
+                     "ucj_unbalanced", "ucj_spinless", "df_matvec", "qdrift",
+                     "basic", "ucj_angles", "ucj_angles_from_ucj", "params_balanced", "params_balanced_from",
+                     "params_unbalanced", "params_spinless", "givens_from_rotation", "qdrift_probs"}
+    assert len(STATE_CASES) >= 150
 
 
 # ----------------------------------------------------------------------------- CPU: pin the oracle
@@ -273,6 +367,87 @@ def test_tables_bit_exact_vs_reference_argsort(name):
         want = c["expected"]
         assert np.array_equal(cistring.one_subspace_indices(norb, nocc, (i,)).astype(np.int64), want)
         assert np.array_equal(np.asarray(prod.one_subspace_indices(norb, nocc, (i,))).astype(np.int64), want)
+
+
+# ----------------------------------------------------------------------------- CPU: host-side product code
+@pytest.mark.parametrize("name", names("params/"))
+def test_parameter_vectors_match_reference(name):
+    """n_params / to_parameters / from_parameters of the UCJ operators (the reference's vector layout)."""
+    import ffsim_b200 as f
+
+    c = CASES[name]
+    kind, norb, n_reps, final = str(c["kind"]), int(c["norb"]), int(c["n_reps"]), bool(c["final"])
+    if kind in ("params_balanced", "params_balanced_from"):
+        pairs = None if opt(c["pairs_aa"]) is None else (_pairs(c["pairs_aa"]), _pairs(c["pairs_ab"]))
+        if kind == "params_balanced":
+            op = f.UCJOpSpinBalanced(c["diag_coulomb_mats"], c["orbital_rotations"], c["final_orbital_rotation"])
+            got = op.to_parameters(interaction_pairs=pairs)
+            assert got.shape == c["expected"].shape and np.allclose(got, c["expected"], rtol=0, atol=1e-12)
+            assert len(got) == f.UCJOpSpinBalanced.n_params(norb, n_reps, interaction_pairs=pairs,
+                                                             with_final_orbital_rotation=final)
+            back = f.UCJOpSpinBalanced.from_parameters(got, norb=norb, n_reps=n_reps, interaction_pairs=pairs,
+                                                       with_final_orbital_rotation=final)
+            assert np.allclose(back.orbital_rotations, op.orbital_rotations, atol=1e-12)
+        else:
+            op = f.UCJOpSpinBalanced.from_parameters(c["params"], norb=norb, n_reps=n_reps, interaction_pairs=pairs,
+                                                     with_final_orbital_rotation=final)
+            assert np.allclose(op.diag_coulomb_mats, c["diag_coulomb_mats"], rtol=0, atol=1e-13)
+            assert np.allclose(op.orbital_rotations, c["orbital_rotations"], rtol=0, atol=1e-12)
+            assert np.allclose(op.final_orbital_rotation, c["final_orbital_rotation"], rtol=0, atol=1e-12)
+    elif kind == "params_unbalanced":
+        op = f.UCJOpSpinUnbalanced(c["diag_coulomb_mats"], c["orbital_rotations"], c["final_orbital_rotation"])
+        got = op.to_parameters()
+        assert len(got) == int(c["n_params"]) == f.UCJOpSpinUnbalanced.n_params(norb, n_reps,
+                                                                                  with_final_orbital_rotation=final)
+        assert np.allclose(got, c["expected"], rtol=0, atol=1e-12)
+        back = f.UCJOpSpinUnbalanced.from_parameters(got, norb=norb, n_reps=n_reps, with_final_orbital_rotation=final)
+        assert np.allclose(back.diag_coulomb_mats, op.diag_coulomb_mats, atol=1e-13)
+        assert np.allclose(back.final_orbital_rotation, op.final_orbital_rotation, atol=1e-12)
+    else:
+        pairs = _pairs(c["pairs"])
+        op = f.UCJOpSpinless(c["diag_coulomb_mats"], c["orbital_rotations"])
+        got = op.to_parameters(interaction_pairs=pairs)
+        assert len(got) == int(c["n_params"]) == f.UCJOpSpinless.n_params(norb, n_reps, interaction_pairs=pairs)
+        assert np.allclose(got, c["expected"], rtol=0, atol=1e-12)
+
+
+def test_parameter_vector_errors():
+    import ffsim_b200 as f
+
+    with pytest.raises(ValueError, match="Expected 36 but got 3"):
+        f.UCJOpSpinBalanced.from_parameters(np.zeros(3), norb=4, n_reps=1)
+    with pytest.raises(ValueError, match="Duplicate interaction pairs"):
+        f.UCJOpSpinBalanced.n_params(4, 1, interaction_pairs=([(0, 1), (0, 1)], None))
+    with pytest.raises(ValueError, match="lower triangular pair"):
+        f.UCJOpSpinless.n_params(4, 1, interaction_pairs=[(2, 1)])
+
+
+def test_givens_ansatz_from_orbital_rotation_matches_reference():
+    """GivensAnsatzOp.from_orbital_rotation: brickwork layout, angles and the rebuilt unitary."""
+    import ffsim_b200 as f
+
+    c = CASES["angles/givens_from_rotation_5"]
+    g = f.GivensAnsatzOp.from_orbital_rotation(c["mat"])
+    assert [tuple(p) for p in g.interaction_pairs] == _pairs(c["pairs"])
+    assert np.allclose(g.thetas, c["thetas"], rtol=0, atol=1e-12)
+    assert np.allclose(g.phis, c["phis"], rtol=0, atol=1e-12)
+    assert np.allclose(g.phase_angles, c["phase_angles"], rtol=0, atol=1e-12)
+    assert np.allclose(g.to_orbital_rotation(), c["rotation"], rtol=0, atol=1e-13)
+    assert np.allclose(g.to_orbital_rotation(), c["mat"], rtol=0, atol=1e-12)
+    back = f.GivensAnsatzOp.from_parameters(g.to_parameters(), norb=5, interaction_pairs=g.interaction_pairs)
+    assert back._approx_eq_(g, 0, 1e-15)
+
+
+@pytest.mark.parametrize("name", names("qdrift_probs/"))
+def test_qdrift_probabilities_match_reference(name):
+    """qdrift_probabilities incl. the Slater-determinant-optimal weights (trotter/qdrift.py:247-348, states/wick.py)."""
+    import ffsim_b200 as f
+
+    c = CASES[name]
+    ham = f.DoubleFactorizedHamiltonian(c["one_body_tensor"], c["diag_coulomb_mats"], c["orbital_rotations"],
+                                        constant=float(c["constant"]), z_representation=bool(c["z"]))
+    got = f.qdrift_probabilities(ham, sampling_method=_text(c["method"]), nelec=nelec_of(c), one_rdm=c["one_rdm"])
+    assert np.allclose(got, c["expected"], rtol=1e-10, atol=1e-13), (got, c["expected"])
 
 
 # ----------------------------------------------------------------------------- GPU: the product
