@@ -105,6 +105,13 @@ __host__ __device__ constexpr int cclass_offset(int w, int mp) {
   return off;
 }
 
+__device__ __forceinline__ unsigned dev_binom(int n, int k) {
+  if (k < 0 || k > n) return 0u;
+  unsigned r = 1;
+  for (int i = 1; i <= k; ++i) r = r * (unsigned)(n - k + i) / (unsigned)i;
+  return r;
+}
+
 // ---------------------------------------------------------------- the 2x2 update
 // x' = c x + s y ; y' = c y - conj(s) x      (12 DFMA-pipe operations)
 __device__ __forceinline__ void zrot(double2 &x, double2 &y, double c, double sr, double si) {
@@ -252,8 +259,15 @@ __host__ __device__ inline size_t fused_smem_gsub_off() { return 2 * kOffTabEntr
 __host__ __device__ inline size_t fused_smem_cend_off(int n_sub) {
   return fused_smem_gsub_off() + (size_t)n_sub * sizeof(GroupSubDev);
 }
-__host__ __device__ inline size_t fused_smem_blk_off(int n_sub) {
+// per (sub-pass, warp) chunk lists of the balanced schedule: kWarpList chunk indices (0xFF = none)
+constexpr int kWarpList = 8;
+constexpr int kMaxWarps = FFB_TPB / 32;
+__host__ __device__ inline size_t fused_smem_wl_off(int n_sub) {
   return fused_smem_cend_off(n_sub) + (size_t)n_sub * kChunkRow * sizeof(uint16_t);
+}
+__host__ __device__ inline size_t fused_smem_blk_off(int n_sub) {
+  // (+1 byte per sub-pass: "list valid" flag; rounded up to 16 bytes for the block-list copies)
+  return (fused_smem_wl_off(n_sub) + (size_t)n_sub * (kMaxWarps * kWarpList + 1) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t fused_smem_tile_off(int n_sub, int blk_cap) {
   return fused_smem_blk_off(n_sub) + 2 * (size_t)blk_cap * sizeof(uint32_t);
@@ -321,6 +335,8 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
   uint32_t *offbuf = reinterpret_cast<uint32_t *>(smem_raw);  // 2 x kOffTabEntries
   GroupSubDev *gsub_s = reinterpret_cast<GroupSubDev *>(smem_raw + fused_smem_gsub_off());
   uint16_t *cend_s = reinterpret_cast<uint16_t *>(smem_raw + fused_smem_cend_off(p.n_sub));
+  uint8_t *wl_s = smem_raw + fused_smem_wl_off(p.n_sub);                 // [n_sub][kMaxWarps][kWarpList]
+  uint8_t *wl_ok_s = wl_s + (size_t)p.n_sub * kMaxWarps * kWarpList;      // [n_sub] 1 = balanced list built
   uint32_t *blkbuf = reinterpret_cast<uint32_t *>(smem_raw + fused_smem_blk_off(p.n_sub));  // 2 x blk_cap
   double2 *tile = reinterpret_cast<double2 *>(smem_raw + fused_smem_tile_off(p.n_sub, p.blk_cap));
   const unsigned tile_sa = (unsigned)__cvta_generic_to_shared(tile);
@@ -422,6 +438,37 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
           }
           row[kChunkRow - 1] = (uint16_t)acc;
         }
+        // Balanced static schedule: chunks of a sub-pass differ in cost by ~5x between classes, and a
+        // sub-pass ends at a CTA barrier, so its duration is the busiest warp's.  Longest-processing-time
+        // first: walk the chunk list (classes are sorted heaviest first) and give every chunk to the warp
+        // with the least work so far.  One warp builds the lists of one sub-pass (lane = target warp).
+        for (int sp = warp; sp < p.n_sub; sp += nwarp) {
+          const GroupSubDev &gsrc = p.gsub[G.gsub_off + sp];
+          const int n_rot_sp = p.sub[sp].rot_end - p.sub[sp].rot_begin;
+          uint8_t *mine = wl_s + ((size_t)sp * kMaxWarps + lane) * kWarpList;
+          unsigned load = 0;
+          int cnt = 0, g = 0;
+          bool ok = nwarp <= kMaxWarps;
+          for (int k = 0; k < gsrc.n_seg && k < kMaxSeg; ++k) {
+            const int mp = gsrc.seg[k].mp;
+            const int n_ch = (gsrc.seg[k].count * cols + 31) >> 5;
+            // cycles, roughly: 12 FP64 operations per rotation and pair at ~2.7 clk, gather + scatter, fixed part
+            const unsigned cost = 32u * n_rot_sp * dev_binom(W - 2, mp - 1) + 16u * dev_binom(W, mp) + 150u;
+            for (int c = 0; c < n_ch; ++c, ++g) {
+              const unsigned key = lane < nwarp ? ((load << 5) | (unsigned)lane) : 0xFFFFFFFFu;
+              const int winner = (int)(__reduce_min_sync(0xFFFFFFFFu, key) & 31u);
+              if (lane == winner) {
+                if (cnt < kWarpList && g < 255) mine[cnt] = (uint8_t)g;
+                ++cnt;
+                load += cost;
+              }
+            }
+          }
+          if (lane < kMaxWarps)
+            for (int c = min(cnt, kWarpList); c < kWarpList; ++c) mine[c] = 0xFF;
+          ok = __all_sync(0xFFFFFFFFu, cnt <= kWarpList) && g <= 255 && ok;
+          if (lane == 0) wl_ok_s[sp] = ok ? 1 : 0;
+        }
       }
     }
     cp_async_wait_all();  // the tile, the first offset table and the first block list
@@ -449,10 +496,21 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
         const uint16_t *cend = cend_s + s * kChunkRow;
         const int run0 = p.sub[s].run_begin, run1 = p.sub[s].run_end;
         const int n_chunks = cend[kChunkRow - 1];
-        int g = warp;
+        // chunk sequence of this warp: the balanced list when it was built, else the static boustrophedon
+        // deal (round k: chunk k * nwarp + warp, reversed on odd k)
+        const bool balanced = wl_ok_s[s] != 0;
+        const uint8_t *mylist = wl_s + ((size_t)s * kMaxWarps + warp) * kWarpList;
+        auto chunk_at = [&](int k) -> int {
+          if (balanced) {
+            const int g = k < kWarpList ? (int)mylist[k] : 0xFF;
+            return g == 0xFF ? n_chunks : g;
+          }
+          return k * nwarp + ((k & 1) ? nwarp - 1 - warp : warp);
+        };
+        int g = chunk_at(0);
         ChunkWork cur = fetch_chunk(gs, cend, blk, g, lane, cols);
         for (int k = 1; g < n_chunks; ++k) {
-          const int g_next = k * nwarp + ((k & 1) ? nwarp - 1 - warp : warp);
+          const int g_next = chunk_at(k);
           ChunkWork nxt;
           nxt.entry = 0;
           nxt.mp = 0;

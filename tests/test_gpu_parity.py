@@ -447,9 +447,20 @@ def test_qdrift_double_factorized():
         ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, n_steps=-1)
     with pytest.raises(ValueError, match="n_samples"):
         ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, n_samples=0)
-    with pytest.raises(NotImplementedError):
-        ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, probabilities="optimal",
-                                                one_rdm=np.eye(2 * norb))
+    # state-dependent probabilities (Wick expectations in the Hartree-Fock determinant): same trajectory as
+    # passing those probabilities explicitly
+    rdm = np.zeros((2 * norb, 2 * norb))
+    for i in list(range(nelec[0])) + [norb + j for j in range(nelec[1])]:
+        rdm[i, i] = 1.0
+    probs_opt = ffsim.qdrift_probabilities(ham, "optimal", nelec=nelec, one_rdm=rdm)
+    assert abs(probs_opt.sum() - 1) < 1e-12 and (probs_opt >= 0).all()
+    got = ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, n_steps=4,
+                                                  probabilities="optimal", one_rdm=rdm, seed=11)
+    want = ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, n_steps=4,
+                                                   probabilities=probs_opt, seed=11)
+    assert rel_err(got, want) <= TOL
+    with pytest.raises(ValueError, match="requires one_rdm"):
+        ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, probabilities="optimal")
 
 
 # ------------------------------------------------------------------ BASELINE shapes: properties
