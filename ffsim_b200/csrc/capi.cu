@@ -297,7 +297,10 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
   for (size_t ip = 0; ip < n_pass; ++ip) {
     DevicePass &dp = *sp.structure->passes[ip];
     const bool last = ip + 1 == n_pass;
-    const size_t overhead = fused_pass_smem_overhead((int)dp.sched.subs.size(), dp.blk_cap);
+    int off_rows = 1;
+    for (const SubPass &sub : dp.sched.subs) off_rows = std::max(off_rows, sub.q0 + 1);
+    off_rows = std::min(off_rows, (int)kMaxLowDev);
+    const size_t overhead = fused_pass_smem_overhead((int)dp.sched.subs.size(), dp.blk_cap, off_rows);
     if (overhead + 64 + 1024 > plan->dev.smem_optin)
       return fail(FFB_EINTERNAL, "pass tables do not fit in shared memory");
     size_t budget = std::min<size_t>((size_t)plan->opt.smem_bytes, plan->dev.smem_optin - overhead - 64);
@@ -314,6 +317,7 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     P.off = dp.d_off;
     P.n_sub = (int)dp.sched.subs.size();
     P.blk_cap = dp.blk_cap;
+    P.off_rows = off_rows;
     P.n_rot = (int)dp.sched.rot_index.size();
     P.w = dp.sched.subs.empty() ? 2 : dp.sched.subs[0].w;
     if (P.n_sub > kMaxSubPerPass || P.n_rot > kMaxRotPerPass)

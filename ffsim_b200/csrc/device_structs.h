@@ -97,7 +97,7 @@ struct PassParams {
   const uint32_t *off;   // [n_sub][kMaxLowDev][kOffRowDev] byte offsets (row offset * 16)
   int n_groups, n_sub, n_rot, w;
   int blk_cap;           // u32 entries of one block-list staging buffer (longest list, multiple of 4)
-  int pad0;
+  int off_rows;          // rows of a sub-pass's offset table that are staged: max q0 + 1 (<= kMaxLowDev)
   long long total_units;
   GroupLaunch g[kMaxGroups];
   SubMeta sub[kMaxSubPerPass];

@@ -255,22 +255,25 @@ static_assert(kOffTabEntries % 4 == 0, "offset tables are copied in 16-byte unit
 
 // shared-memory prefix of the kernel: two block-offset tables, the group's per-sub-pass segment
 // descriptors, their chunk prefixes and two block-list staging buffers
-__host__ __device__ inline size_t fused_smem_gsub_off() { return 2 * kOffTabEntries * sizeof(uint32_t); }
-__host__ __device__ inline size_t fused_smem_cend_off(int n_sub) {
-  return fused_smem_gsub_off() + (size_t)n_sub * sizeof(GroupSubDev);
+// (only the first off_rows = max q0 + 1 rows of a sub-pass's offset table are ever addressed)
+__host__ __device__ inline size_t fused_smem_gsub_off(int off_rows) {
+  return 2 * (size_t)off_rows * kOffRowDev * sizeof(uint32_t);
+}
+__host__ __device__ inline size_t fused_smem_cend_off(int n_sub, int off_rows) {
+  return fused_smem_gsub_off(off_rows) + (size_t)n_sub * sizeof(GroupSubDev);
 }
 // per (sub-pass, warp) chunk lists of the balanced schedule: kWarpList chunk indices (0xFF = none)
 constexpr int kWarpList = 8;
 constexpr int kMaxWarps = FFB_TPB / 32;
-__host__ __device__ inline size_t fused_smem_wl_off(int n_sub) {
-  return fused_smem_cend_off(n_sub) + (size_t)n_sub * kChunkRow * sizeof(uint16_t);
+__host__ __device__ inline size_t fused_smem_wl_off(int n_sub, int off_rows) {
+  return fused_smem_cend_off(n_sub, off_rows) + (size_t)n_sub * kChunkRow * sizeof(uint16_t);
 }
-__host__ __device__ inline size_t fused_smem_blk_off(int n_sub) {
+__host__ __device__ inline size_t fused_smem_blk_off(int n_sub, int off_rows) {
   // (+1 byte per sub-pass: "list valid" flag; rounded up to 16 bytes for the block-list copies)
-  return (fused_smem_wl_off(n_sub) + (size_t)n_sub * (kMaxWarps * kWarpList + 1) + 15) & ~(size_t)15;
+  return (fused_smem_wl_off(n_sub, off_rows) + (size_t)n_sub * (kMaxWarps * kWarpList + 1) + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t fused_smem_tile_off(int n_sub, int blk_cap) {
-  return fused_smem_blk_off(n_sub) + 2 * (size_t)blk_cap * sizeof(uint32_t);
+__host__ __device__ inline size_t fused_smem_tile_off(int n_sub, int blk_cap, int off_rows) {
+  return fused_smem_blk_off(n_sub, off_rows) + 2 * (size_t)blk_cap * sizeof(uint32_t);
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, no stall at issue
@@ -332,13 +335,14 @@ template <int W>
 __global__ void __launch_bounds__(FFB_TPB, 1)
     fused_pass_kernel(const __grid_constant__ PassParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t *offbuf = reinterpret_cast<uint32_t *>(smem_raw);  // 2 x kOffTabEntries
-  GroupSubDev *gsub_s = reinterpret_cast<GroupSubDev *>(smem_raw + fused_smem_gsub_off());
-  uint16_t *cend_s = reinterpret_cast<uint16_t *>(smem_raw + fused_smem_cend_off(p.n_sub));
-  uint8_t *wl_s = smem_raw + fused_smem_wl_off(p.n_sub);                 // [n_sub][kMaxWarps][kWarpList]
+  const int off_entries = p.off_rows * kOffRowDev;  // u32 entries of one staged offset table
+  uint32_t *offbuf = reinterpret_cast<uint32_t *>(smem_raw);  // 2 x off_entries
+  GroupSubDev *gsub_s = reinterpret_cast<GroupSubDev *>(smem_raw + fused_smem_gsub_off(p.off_rows));
+  uint16_t *cend_s = reinterpret_cast<uint16_t *>(smem_raw + fused_smem_cend_off(p.n_sub, p.off_rows));
+  uint8_t *wl_s = smem_raw + fused_smem_wl_off(p.n_sub, p.off_rows);     // [n_sub][kMaxWarps][kWarpList]
   uint8_t *wl_ok_s = wl_s + (size_t)p.n_sub * kMaxWarps * kWarpList;      // [n_sub] 1 = balanced list built
-  uint32_t *blkbuf = reinterpret_cast<uint32_t *>(smem_raw + fused_smem_blk_off(p.n_sub));  // 2 x blk_cap
-  double2 *tile = reinterpret_cast<double2 *>(smem_raw + fused_smem_tile_off(p.n_sub, p.blk_cap));
+  uint32_t *blkbuf = reinterpret_cast<uint32_t *>(smem_raw + fused_smem_blk_off(p.n_sub, p.off_rows));  // 2 x blk_cap
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw + fused_smem_tile_off(p.n_sub, p.blk_cap, p.off_rows));
   const unsigned tile_sa = (unsigned)__cvta_generic_to_shared(tile);
   const unsigned off_sa = (unsigned)__cvta_generic_to_shared(offbuf);
 
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
     const bool work = G.has_blocks && p.n_sub > 0;
     if (work) {
       // first sub-pass: block-offset table and block list
-      for (int e = tid; e < kOffTabEntries / 4; e += nthr) cp_async16(offbuf + 4 * e, p.off + 4 * e);
+      for (int e = tid; e < off_entries / 4; e += nthr) cp_async16(offbuf + 4 * e, p.off + 4 * e);
       {
         const GroupSubDev &g0 = p.gsub[G.gsub_off];
         const uint32_t *src = p.u32 + g0.blocks_off;
@@ -481,12 +485,12 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
     // keeps the warps balanced at the barrier without any shared counter.
     if (work) {
       for (int s = 0; s < p.n_sub; ++s) {
-        const unsigned offtab_sa = off_sa + (unsigned)((s & 1) * kOffTabEntries * sizeof(uint32_t));
+        const unsigned offtab_sa = off_sa + (unsigned)((s & 1) * off_entries * sizeof(uint32_t));
         const uint32_t *blk = blkbuf + (s & 1) * p.blk_cap;
         if (s + 1 < p.n_sub) {  // stage the next sub-pass's tables (they land before the barrier)
-          uint32_t *dst = offbuf + ((s + 1) & 1) * kOffTabEntries;
+          uint32_t *dst = offbuf + ((s + 1) & 1) * off_entries;
           const uint32_t *src = p.off + (size_t)(s + 1) * kOffTabEntries;
-          for (int e = tid; e < kOffTabEntries / 4; e += nthr) cp_async16(dst + 4 * e, src + 4 * e);
+          for (int e = tid; e < off_entries / 4; e += nthr) cp_async16(dst + 4 * e, src + 4 * e);
           const GroupSubDev &gn = gsub_s[s + 1];
           uint32_t *bdst = blkbuf + ((s + 1) & 1) * p.blk_cap;
           const uint32_t *bsrc = p.u32 + gn.blocks_off;
@@ -619,7 +623,9 @@ static cudaError_t launch_w(const PassParams &p, int grid, int threads, size_t s
   return cudaGetLastError();
 }
 
-size_t fused_pass_smem_overhead(int n_sub, int blk_cap) { return fused_smem_tile_off(n_sub, blk_cap); }
+size_t fused_pass_smem_overhead(int n_sub, int blk_cap, int off_rows) {
+  return fused_smem_tile_off(n_sub, blk_cap, off_rows);
+}
 
 template <int W>
 static int occupancy_w(int threads, size_t smem) {

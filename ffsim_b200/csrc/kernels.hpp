@@ -12,8 +12,9 @@ struct PhaseList {  // per-orbital phases passed by value
 };
 
 // shared memory the fused kernel needs besides the tile: offset tables, segment descriptors of
-// `n_sub` sub-passes and two block-list staging buffers of `blk_cap` entries
-size_t fused_pass_smem_overhead(int n_sub, int blk_cap);
+// `n_sub` sub-passes, two block-list staging buffers of `blk_cap` entries and two offset tables of
+// `off_rows` rows (the largest register-block start position of the pass, plus one)
+size_t fused_pass_smem_overhead(int n_sub, int blk_cap, int off_rows);
 int fused_pass_ctas_per_sm(int w, int threads, size_t smem_bytes);
 cudaError_t launch_fused_pass(const PassParams &p, int grid, int threads, size_t smem_bytes,
                               cudaStream_t stream);

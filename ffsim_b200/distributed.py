@@ -27,7 +27,8 @@ final place in the destination GPU's buffer: one kernel, no staging.  Otherwise 
 (``ffb_exchange_blocks`` with local destinations); on CPU tensors (``gloo``: how the host-side logic is
 tested without GPUs) the pack / unpack are plain tensor copies.  ``FFSIM_B200_EXCHANGE`` = ``p2p`` /
 ``nccl`` forces one of them, ``auto`` (default) takes the peer-memory path up to
-``FFSIM_B200_P2P_MAX_WORLD`` ranks (default 2, the validated configuration).
+``FFSIM_B200_P2P_MAX_WORLD`` ranks (default 8) and ``FFSIM_B200_P2P_MAX_GB`` per symmetric buffer (default 16):
+the configurations measured on this pool (2, 4 and 8 ranks of a 16 GB state).
 """
 
 from __future__ import annotations
@@ -369,8 +370,11 @@ def p2p_available(sv: "ShardedVector") -> bool:
     if sv.world == 1 or sv.world > 16 or not sv.device.type == "cuda":
         return False
     mode = os.environ.get("FFSIM_B200_EXCHANGE", "auto").lower()
-    max_world = int(os.environ.get("FFSIM_B200_P2P_MAX_WORLD", "2"))
-    if mode == "nccl" or (mode != "p2p" and sv.world > max_world):
+    # "auto": the configurations validated on this pool -- up to 8 ranks (2, 4, 8 measured) and symmetric
+    # buffers up to 16 GB per rank (8 GB measured); larger shards (the 254 GB state: 32 GB) go through NCCL
+    max_world = int(os.environ.get("FFSIM_B200_P2P_MAX_WORLD", "8"))
+    max_bytes = int(os.environ.get("FFSIM_B200_P2P_MAX_GB", "16")) << 30
+    if mode == "nccl" or (mode != "p2p" and (sv.world > max_world or 16 * _symm_numel(sv) > max_bytes)):
         return False
     if not _SYMM_STATE["checked"]:
         ok = 1

@@ -128,6 +128,7 @@ def main():
     hf = ShardedVector.hartree_fock(norb, nelec, device=dev)
     u = op.orbital_rotations[0]
     rot = ffsim.apply_orbital_rotation(hf, u, norb, nelec, copy=False)
+    rot.set_layout(distributed.ROWS)  # the check below walks the row shard
     ma, mb = slater_minors(u, norb, nelec[0]), slater_minors(u, norb, nelec[1])
     # outer(ma[rows], mb) is built on the device in row blocks (the full product is shard-sized)
     ma_d = torch.from_numpy(ma[rot.row0:rot.row0 + rot.n_rows]).to(dev)
@@ -146,11 +147,11 @@ def main():
     torch.cuda.empty_cache()
 
     times = []
-    state = ShardedVector.hartree_fock(norb, nelec, device=dev)
+    state = None
     for it in range(args.steps + 1):
-        state.local.zero_()
-        if state.row0 == 0:
-            state.local[0] = 1
+        del state  # (the previous result may sit in the column distribution: start from a fresh row shard)
+        state = ShardedVector.hartree_fock(norb, nelec, device=dev)
+        distributed.STATS.update(exchanges=0, bytes_sent=0)
         sync()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -169,10 +170,28 @@ def main():
            "plan": get_plan(norb, nelec, op.orbital_rotations[0], op.orbital_rotations[0]).describe(),
            "peak_device_GB": torch.cuda.max_memory_allocated() / 1e9,
            "rotation_parity_vs_slater_minors": parity,
-           "all_to_all_per_rotation": 2, "nvlink_bytes_per_rank_per_all_to_all": distributed.all_to_all_bytes(state),
+           "all_to_all_per_application": distributed.STATS["exchanges"], "exchange": distributed.STATS["mode"],
+           "nvlink_bytes_sent_per_rank_per_application": distributed.STATS["bytes_sent"],
            "algorithmic_hbm_bytes_total": ((args.n_reps + 1) * 64 + args.n_reps * 32) * dim}
-    n_a2a = 2 * (args.n_reps + 1)
-    out["nvlink_GBps_if_comm_bound"] = n_a2a * out["nvlink_bytes_per_rank_per_all_to_all"] / (out["ms"] * 1e-3) / 1e9
+    # the three floors of the application, side by side (whole job over all ranks)
+    import math
+
+    from ffsim_b200 import _lib
+    from ffsim_b200.linalg import givens_decomposition
+
+    n_rot = sum(len(givens_decomposition(np.asarray(m))[0]) for m in
+                [op.orbital_rotations[0].T.conj()] +
+                [op.orbital_rotations[k + 1].T.conj() @ op.orbital_rotations[k] for k in range(args.n_reps - 1)] +
+                [op.orbital_rotations[-1]])
+    pairs = (math.comb(norb - 2, nelec[0] - 1) * math.comb(norb, nelec[1])
+             + math.comb(norb - 2, nelec[1] - 1) * math.comb(norb, nelec[0]))
+    fp64_peak = _lib.measure_fp64_peak()
+    out["floors_ms"] = {
+        "fp64": 2.0 * 12.0 * n_rot * pairs / (world * fp64_peak * 1e12) * 1e3,
+        "hbm": out["algorithmic_hbm_bytes_total"] / (world * 6465.2e9) * 1e3,
+        "nvlink": out["nvlink_bytes_sent_per_rank_per_application"] / 770e9 * 1e3,
+        "fp64_peak_tflops_per_gpu": fp64_peak, "rotations_per_spin_total": n_rot}
+    out["nvlink_GBps_if_comm_bound"] = out["nvlink_bytes_sent_per_rank_per_application"] / (out["ms"] * 1e-3) / 1e9
     out["algorithmic_TBps_total"] = out["algorithmic_hbm_bytes_total"] / (out["ms"] * 1e-3) / 1e12
     if args.energy:
         ham = ffsim.random.random_diagonal_coulomb_hamiltonian(norb, seed=2405)
