@@ -26,6 +26,7 @@ from ffsim_b200.gates import (
 )
 from ffsim_b200.hamiltonians import DiagonalCoulombHamiltonian, DoubleFactorizedHamiltonian
 from ffsim_b200.init_cache import init_cache
+from ffsim_b200.pipeline import evolve_host, pinned_empty
 from ffsim_b200.protocols import apply_unitary, linear_operator
 from ffsim_b200.states import Spin, dim, dims, hartree_fock_state
 from ffsim_b200.trotter import (
@@ -90,6 +91,7 @@ __all__ = [
     "contract_diag_coulomb",
     "contract_num_op_sum",
     "diag_coulomb_linop",
+    "evolve_host",
     "dim",
     "dims",
     "hartree_fock_state",
@@ -97,6 +99,7 @@ __all__ = [
     "linalg",
     "linear_operator",
     "num_op_sum_linop",
+    "pinned_empty",
     "qdrift_probabilities",
     "random",
     "simulate_qdrift_double_factorized",

@@ -104,6 +104,7 @@ EXPORTS = {
     "ffb_axpby": (c_int, C128, _P, C128, _P, c_int64, _P),
     "ffb_profile_begin": (c_int,),
     "ffb_profile_end": (c_int, c_char_p, c_size_t),
+    "ffb_memcpy2d_async": (c_int, _P, c_size_t, _P, c_size_t, c_size_t, c_size_t, c_int, _P),
     "ffb_measure_fp64_peak": (c_int, POINTER(c_double)),
     "ffb_set_option": (c_int, c_char_p, c_int64),
     "ffb_get_option": (c_int64, c_char_p),

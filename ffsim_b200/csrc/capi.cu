@@ -913,6 +913,19 @@ int ffb_apply_num_op_prod_phase(ffb_tables *tables_a, ffb_tables *tables_b, uint
   return FFB_OK;
 }
 
+int ffb_memcpy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes,
+                       size_t height, int kind, void *stream) {
+  if (width_bytes == 0 || height == 0) return FFB_OK;
+  if (!dst || !src || kind < 1 || kind > 3 || (height > 1 && (dst_pitch < width_bytes || src_pitch < width_bytes)))
+    return fail(FFB_EINVAL, "ffb_memcpy2d_async: bad argument");
+  const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+  if (height == 1)
+    FFB_CUDA(cudaMemcpyAsync(dst, src, width_bytes, k, (cudaStream_t)stream));
+  else
+    FFB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height, k, (cudaStream_t)stream));
+  return FFB_OK;
+}
+
 int ffb_measure_fp64_peak(double *tflops) {
   if (!tflops) return fail(FFB_EINVAL, "ffb_measure_fp64_peak: NULL argument");
   DeviceInfo di;

@@ -612,12 +612,15 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
 template <int W>
 static cudaError_t launch_w(const PassParams &p, int grid, int threads, size_t smem,
                             cudaStream_t stream) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(fused_pass_kernel<W>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the opt-in shared-memory size is an attribute of the function ON ONE DEVICE: remember it per device
+  static size_t configured[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+    e = cudaFuncSetAttribute(fused_pass_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
   }
   fused_pass_kernel<W><<<grid, threads, smem, stream>>>(p);
   return cudaGetLastError();

@@ -64,6 +64,9 @@ int ffb_set_device(int device);
  * gen_occslst) and the cached address tables of
  * python/ffsim/gates/orbital_rotation.py:203-236.  Host side is built at
  * creation; the device copy is made on first use by a device entry point. */
+/* Limits: 0 <= nocc <= norb <= 64 on the host side, norb <= 32 for every device entry point (strings
+ * are held in 32 bits there) and fewer than 2^31 strings per sector; violations return FFB_EINVAL.  A
+ * handle owns device buffers (strings, per-call scratch): use one handle per device and per stream. */
 int ffb_tables_create(int norb, int nocc, ffb_tables **out);
 void ffb_tables_destroy(ffb_tables *t);
 int64_t ffb_tables_dim(const ffb_tables *t);
@@ -242,6 +245,13 @@ int ffb_axpby(ffb_c128 alpha, const void *x_dev, ffb_c128 beta, void *y_dev, int
  * (bytes = algorithmic bytes of the timed launches). */
 int ffb_profile_begin(void);
 int ffb_profile_end(char *buf, size_t buflen);
+
+/* Asynchronous strided copy (cudaMemcpy2DAsync; kind 1 = host to device, 2 = device to host, 3 = device to
+ * device): `height` rows of `width_bytes`, row pitches in bytes.  It moves a column strip or a row block of
+ * a HOST state to / from the device while the kernels work on the strips that have already arrived
+ * (ffsim_b200/pipeline.py); the host side should be page-locked. */
+int ffb_memcpy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes,
+                       size_t height, int kind, void *stream);
 
 /* Dense FP64 FMA throughput of the current device in TFLOP/s (a short microbenchmark, ~10 ms): the
  * second roofline denominator of the fused rotation kernel, measured where the bench runs. */

@@ -49,9 +49,13 @@ def c1():
     want = cref.ucj_spin_balanced_apply(hf, op.diag_coulomb_mats, op.orbital_rotations, op.final_orbital_rotation,
                                         norb, nelec)
     cpu_ms = (time.perf_counter() - t0) * 1e3
-    t0 = time.perf_counter()
-    ffsim.apply_unitary(hf, op, norb=norb, nelec=nelec)
-    api_ms = (time.perf_counter() - t0) * 1e3
+    api = []
+    for _ in range(7):  # steady state: the first calls pin the pooled host buffers
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ffsim.apply_unitary(hf, op, norb=norb, nelec=nelec)
+        api.append((time.perf_counter() - t0) * 1e3)
+    api_ms = float(np.median(api[2:]))
     alg = ((L + 1) * 64 + L * 32) * dim
     return {"config": "C1: LUCJ n_reps=2 on Hartree-Fock, norb=12 nelec=(6,6), 853,776 amplitudes",
             "device_ms": ms, "public_api_numpy_ms": api_ms, "applications_per_s": 1e3 / ms,

@@ -69,8 +69,12 @@ if os.path.exists(launches):
     md.append("")
 
 rep = os.path.join(G, f"{tag}_prof.ncu-rep")
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw_csv = os.path.join(G, f"{tag}_raw.csv")  # extracted on the GPU box when the report is too large to bring back
+if os.path.exists(rep) or os.path.exists(raw_csv):
+    if os.path.exists(raw_csv) and os.path.getsize(raw_csv) > 0:
+        raw = open(raw_csv).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     cols = [hdr.index("Kernel Name")] + [hdr.index(k) for k in KEEP if k in hdr]

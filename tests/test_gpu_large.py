@@ -212,3 +212,37 @@ def test_trotter_step_twin_norb14_multipass():
     want = cref.apply_orbital_rotation(want, basis, norb, nelec, copy=False)
     want = want * np.exp(-1j * 0.25 * df.constant)
     assert rel_err(got, want) < TOL
+
+
+def _wick_energy(one_body, jaa, jab, constant, u, n_alpha, n_beta):
+    """<H> of the determinant U|HF> from its one-body density matrices (closed form, O(norb^2)):
+    SURVEY.md section 8d, the C5 check."""
+    pa = u[:, :n_alpha] @ u[:, :n_alpha].conj().T
+    pb = u[:, :n_beta] @ u[:, :n_beta].conj().T
+    e = constant + np.trace(one_body @ pa).real + np.trace(one_body @ pb).real
+    for p_ in (pa, pb):  # same spin: <n_p n_q> = P_pp P_qq - |P_pq|^2 (p != q), P_pp (p == q)
+        d = np.real(np.diag(p_))
+        nn = np.outer(d, d) - np.abs(p_) ** 2
+        np.fill_diagonal(nn, d)
+        e += 0.5 * np.sum(jaa * nn)
+    da, db = np.real(np.diag(pa)), np.real(np.diag(pb))
+    e += 0.5 * np.sum(jab * (np.outer(da, db) + np.outer(db, da)))
+    return float(e)
+
+
+@pytest.mark.parametrize("norb,nelec", [(10, (3, 4)), (16, (4, 4)), (20, (3, 3))])
+def test_dc_hamiltonian_energy_c5_twins(norb, nelec):
+    """BASELINE configs[4] (DiagonalCoulombHamiltonian energy of a rotated determinant, norb=24 (6,6)) at
+    shapes one GPU holds: <psi|H|psi> through linear_operator on the device against the closed form from
+    the determinant's density matrices -- independent of every kernel and of the oracle."""
+    import torch
+
+    ham = ffsim.random.random_diagonal_coulomb_hamiltonian(norb, seed=2405)
+    u = ffsim.random.random_unitary(norb, seed=2406)
+    state = ffsim.hartree_fock_state(norb, nelec, device="cuda")
+    state = ffsim.apply_orbital_rotation(state, u, norb, nelec, copy=False)
+    hv = ffsim.linear_operator(ham, norb=norb, nelec=nelec) @ state
+    energy = float(torch.vdot(state, hv).real)
+    want = _wick_energy(np.asarray(ham.one_body_tensor), *np.asarray(ham.diag_coulomb_mats), ham.constant, u, *nelec)
+    assert abs(energy - want) <= 1e-10 * max(1.0, abs(want)), (energy, want)
+    assert abs(float(torch.linalg.vector_norm(state)) - 1.0) < 1e-12

@@ -463,6 +463,52 @@ def test_qdrift_double_factorized():
         ffsim.simulate_qdrift_double_factorized(vec, ham, 0.4, norb=norb, nelec=nelec, probabilities="optimal")
 
 
+# ------------------------------------------------------------------ host-resident states (streamed copies)
+
+@pytest.mark.parametrize("opts", [{}, {"smem_bytes": 16 * 1024, "beta_mode": 2}])
+@pytest.mark.parametrize("n_chunks", [1, 3, 7])
+def test_evolve_host_matches_sequential_calls(opts, n_chunks):
+    """ffsim_b200.evolve_host (column strips in, row blocks out, kernels overlapped with the copies) against
+    the same public functions called one after the other, single-pass and multi-pass/transposed plans."""
+    for k, v in opts.items():
+        _lib.set_option(k, v)
+    norb, nelec = 10, (5, 4)
+    rng = np.random.default_rng(1010)
+    vec = _state(norb, nelec, rng)
+    u1, u2 = rand.random_unitary(norb, seed=rng), rand.random_unitary(norb, seed=rng)
+    mat = rand.random_real_symmetric_matrix(norb, seed=rng)
+    coeffs = rng.standard_normal(norb)
+    pinned = ffsim.pinned_empty(vec.size)
+    pinned[:] = vec
+    cases = [
+        [("orbital_rotation", u1), ("diag_coulomb", mat, 0.3)],                       # the bench's step
+        [("diag_coulomb", mat, 0.3, True)],                                           # everything column-local
+        [("orbital_rotation", (u1, None))], [("orbital_rotation", (None, u2))],
+        [("orbital_rotation", u1), ("diag_coulomb", (mat, mat + 0.2, None), 0.1), ("orbital_rotation", (u2, u1)),
+         ("num_op_sum", coeffs, 0.7)],
+        [("num_op_sum", (coeffs, None), 0.2), ("orbital_rotation", u2)],
+    ]
+    for steps in cases:
+        want = vec
+        for step in steps:
+            if step[0] == "orbital_rotation":
+                want = ffsim.apply_orbital_rotation(want, step[1], norb, nelec)
+            elif step[0] == "diag_coulomb":
+                want = ffsim.apply_diag_coulomb_evolution(want, step[1], step[2], norb, nelec,
+                                                          z_representation=len(step) > 3 and step[3])
+            else:
+                want = ffsim.apply_num_op_sum_evolution(want, step[1], step[2], norb, nelec)
+        for src in (pinned, vec):
+            before = src.copy()
+            got = ffsim.evolve_host(src, steps, norb, nelec, n_chunks=n_chunks)
+            assert np.array_equal(src, before), "the input must not be modified"
+            assert rel_err(got, want) <= TOL, (steps[0][0], len(steps), n_chunks, rel_err(got, want))
+    with pytest.raises(ValueError, match="unknown step"):
+        ffsim.evolve_host(vec, [("rotate", u1)], norb, nelec)
+    with pytest.raises(ValueError, match="entries"):
+        ffsim.evolve_host(vec[:-1], [("orbital_rotation", u1)], norb, nelec)
+
+
 # ------------------------------------------------------------------ BASELINE shapes: properties
 
 def test_c2_shape_against_c_oracle_and_properties():
