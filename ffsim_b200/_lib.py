@@ -87,6 +87,7 @@ EXPORTS = {
     "ffb_apply_orbital_rotation_rows": (c_int, _P, c_int, _P, c_int64, c_int64, _P),
     "ffb_apply_orbital_rotation_strided": (c_int, _P, c_int, _P, c_int64, c_int64, c_int64, _P),
     "ffb_plan_beta_in_place": (c_int, _P),
+    "ffb_apply_orbital_rotation_beta_block": (c_int, _P, _P, c_int64, c_int64, _P, _P),
     "ffb_apply_diag_coulomb_evolution": (c_int, _P, _P, _P, _P, _P, c_int, _P, c_int64, c_int64, _P),
     "ffb_apply_num_op_sum_evolution": (c_int, _P, _P, _P, _P, _P, c_int64, c_int64, _P),
     "ffb_contract_diag_coulomb": (c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int64, c_int64, _P),

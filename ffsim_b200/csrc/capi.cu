@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -273,8 +274,17 @@ int setup_side(ffb_plan *plan, int which, ffb_tables *t, const ffb_givens_rotati
 
 // Rotate the string index of a (dim x n_cols) matrix: element (r, c) lives at
 // data[r * row_stride + c * col_stride].
+// The other layout of the same matrix, for the first / last pass of a beta-side rotation that works on
+// a transposed copy: the first pass may read its tiles from `ptr` (instead of `data`) and the last
+// pass may write them to `ptr`, which folds the two transpositions into those passes.
+struct AltLayout {
+  void *ptr = nullptr;
+  int64_t row_stride = 0, col_stride = 0;
+  bool read_first = false, write_last = false;
+};
+
 int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t row_stride,
-               int64_t col_stride, cudaStream_t stream) {
+               int64_t col_stride, cudaStream_t stream, const AltLayout &alt = AltLayout()) {
   SidePlan &sp = plan->side[which];
   if (!sp.active || n_cols <= 0 || sp.tables->dim <= 0) return FFB_OK;
   const int64_t dim = sp.tables->dim;
@@ -309,6 +319,19 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     P.data = data;
     P.row_stride = row_stride;
     P.col_stride = col_stride;
+    P.out = data;
+    P.out_row_stride = row_stride;
+    P.out_col_stride = col_stride;
+    if (alt.ptr && alt.read_first && ip == 0) {
+      P.data = alt.ptr;
+      P.row_stride = alt.row_stride;
+      P.col_stride = alt.col_stride;
+    }
+    if (alt.ptr && alt.write_last && last) {
+      P.out = alt.ptr;
+      P.out_row_stride = alt.row_stride;
+      P.out_col_stride = alt.col_stride;
+    }
     P.n_cols = n_cols;
     P.rowphase = (last && sp.has_phases) ? sp.d_rowphase : nullptr;
     P.u32 = dp.d_u32;
@@ -351,7 +374,8 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     size_t tile_bytes = 0;
     for (size_t gi = 0; gi < dp.host.groups.size(); ++gi) {
       const PassGroupHost &G = dp.host.groups[gi];
-      if (!G.has_blocks && !P.rowphase) continue;  // nothing to do for these rows in this pass
+      // nothing to do for these rows in this pass (an out-of-place pass still has to move them)
+      if (!G.has_blocks && !P.rowphase && P.out == P.data) continue;
       if (ng >= kMaxGroups) return fail(FFB_EINTERNAL, "too many tile groups");
       int64_t fit = std::max<int64_t>(1, budget_amps / (G.R + 7));  // tile columns are up to R + 7 apart
       int64_t cols;
@@ -387,6 +411,11 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     // persistent grid: every CTA resident at once (registers, shared memory and threads counted)
     const int ctas_per_sm = fused_pass_ctas_per_sm(P.w, plan->opt.threads, tile_bytes + overhead);
     const int grid = (int)std::min<long long>(units, (long long)plan->dev.sm_count * ctas_per_sm);
+    static const bool trace = std::getenv("FFB_TRACE_LAUNCH") != nullptr;  // developer aid
+    if (trace)
+      std::fprintf(stderr, "[ffb] fused pass %zu: w=%d subs=%d rots=%d groups=%d units=%lld grid=%d (%d CTA/SM) threads=%d smem=%zu (tile %zu + tables %zu) cols[0]=%d\n",
+                   ip, P.w, P.n_sub, P.n_rot, ng, units, grid, ctas_per_sm, plan->opt.threads, tile_bytes + overhead,
+                   tile_bytes, overhead, P.g[0].cols);
     {
       // FP64-pipe work of the pass: 4 DMUL + 8 DFMA per rotation and amplitude pair
       const double pairs = (double)binom(sp.tables->norb - 2, sp.tables->nocc - 1) * (double)n_cols;
@@ -395,6 +424,22 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
     }
   }
   return FFB_OK;
+}
+
+// A beta-side rotation on a transposed copy needs no separate transposition before its first pass
+// when that pass's window starts at orbital 0: its tiles are then contiguous runs of the beta index, so
+// the pass reads them from the native layout (coalesced) and writes them transposed.  Likewise after
+// the last pass.  (With a single pass both would hold and the rotation would simply be in place in the
+// native layout, which the planner has already decided against.)
+bool beta_first_fused(const ffb_plan *p) {
+  const SidePlan &sb = p->side[1];
+  if (!p->beta_transposed || p->opt.beta_mode == 3 || !sb.structure || sb.structure->passes.size() < 2) return false;
+  return sb.structure->passes.front()->sched.lo == 0;
+}
+bool beta_last_fused(const ffb_plan *p) {
+  const SidePlan &sb = p->side[1];
+  if (!p->beta_transposed || p->opt.beta_mode == 3 || !sb.structure || sb.structure->passes.size() < 2) return false;
+  return sb.structure->passes.back()->sched.lo == 0;
 }
 
 }  // namespace
@@ -439,7 +484,7 @@ int ffb_plan_orbital_rotation(ffb_tables *tables_a, ffb_tables *tables_b,
   const SidePlan &sb = plan->side[1];
   bool transposed = false;
   if (sb.active && sb.structure && !sb.structure->passes.empty()) {
-    if (plan->opt.beta_mode == 2) {
+    if (plan->opt.beta_mode >= 2) {
       transposed = true;
     } else if (plan->opt.beta_mode == 0) {
       const bool one_window = sb.structure->passes.size() == 1 &&
@@ -517,7 +562,7 @@ int ffb_plan_n_state_passes(const ffb_plan *p) {
     size_t np = sp.structure ? sp.structure->passes.size() : 0;
     n += np ? (int)np : (sp.has_phases ? 1 : 0);
   }
-  if (p->beta_transposed) n += 2;
+  if (p->beta_transposed) n += (beta_first_fused(p) ? 0 : 1) + (beta_last_fused(p) ? 0 : 1);
   return n;
 }
 
@@ -572,6 +617,36 @@ int ffb_apply_orbital_rotation_strided(ffb_plan *p, int side, void *data_dev, in
 
 int ffb_plan_beta_in_place(const ffb_plan *p) { return p && !p->beta_transposed ? 1 : 0; }
 
+int ffb_apply_orbital_rotation_beta_block(ffb_plan *p, void *block_dev, int64_t n_rows, int64_t ld,
+                                          void *workspace_dev, void *stream) {
+  if (!p) return fail(FFB_EINVAL, "ffb_apply_orbital_rotation_beta_block: NULL plan");
+  if (n_rows < 0 || ld < p->dim_b) return fail(FFB_EINVAL, "ffb_apply_orbital_rotation_beta_block: bad block shape");
+  if (!p->side[1].active || n_rows == 0 || p->dim_b == 0) return FFB_OK;
+  if (!block_dev) return fail(FFB_EINVAL, "ffb_apply_orbital_rotation_beta_block: NULL block");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = ensure_device_strings(p->side[1].tables)) != FFB_OK) return rc;
+  if (!p->beta_transposed) return apply_side(p, 1, block_dev, n_rows, 1, ld, st);
+  if (!workspace_dev) return fail(FFB_EINVAL, "ffb_apply_orbital_rotation_beta_block: this plan needs a workspace");
+  const double tbytes = 32.0 * (double)n_rows * (double)p->dim_b;
+  AltLayout alt;
+  alt.ptr = block_dev;
+  alt.row_stride = 1;  // consecutive beta strings are adjacent in the native layout
+  alt.col_stride = ld;
+  alt.read_first = beta_first_fused(p);
+  alt.write_last = beta_last_fused(p);
+  if (!alt.read_first) {
+    ProfScope prof(kProfTranspose, tbytes, st);
+    FFB_CUDA(launch_transpose(block_dev, workspace_dev, n_rows, p->dim_b, ld, n_rows, p->dev.sm_count, st));
+  }
+  if ((rc = apply_side(p, 1, workspace_dev, n_rows, n_rows, 1, st, alt)) != FFB_OK) return rc;
+  if (!alt.write_last) {
+    ProfScope prof(kProfTranspose, tbytes, st);
+    FFB_CUDA(launch_transpose(workspace_dev, block_dev, p->dim_b, n_rows, n_rows, ld, p->dev.sm_count, st));
+  }
+  return FFB_OK;
+}
+
 int ffb_apply_orbital_rotation(ffb_plan *p, void *vec_dev, void *workspace_dev, void *stream) {
   if (!p) return fail(FFB_EINVAL, "ffb_apply_orbital_rotation: NULL plan");
   if (p->dim_a * p->dim_b == 0) return FFB_OK;
@@ -581,22 +656,7 @@ int ffb_apply_orbital_rotation(ffb_plan *p, void *vec_dev, void *workspace_dev, 
   for (int s = 0; s < 2; ++s)
     if (p->side[s].active && (rc = ensure_device_strings(p->side[s].tables)) != FFB_OK) return rc;
   if ((rc = apply_side(p, 0, vec_dev, p->dim_b, p->dim_b, 1, st)) != FFB_OK) return rc;
-  if (!p->side[1].active) return FFB_OK;
-  if (!p->beta_transposed) return apply_side(p, 1, vec_dev, p->dim_a, 1, p->dim_b, st);
-  if (!workspace_dev) return fail(FFB_EINVAL, "ffb_apply_orbital_rotation: this plan needs a workspace");
-  const double tbytes = 32.0 * (double)p->dim_a * (double)p->dim_b;
-  {
-    ProfScope prof(kProfTranspose, tbytes, st);
-    FFB_CUDA(launch_transpose(vec_dev, workspace_dev, p->dim_a, p->dim_b, p->dim_b, p->dim_a,
-                              p->dev.sm_count, st));
-  }
-  if ((rc = apply_side(p, 1, workspace_dev, p->dim_a, p->dim_a, 1, st)) != FFB_OK) return rc;
-  {
-    ProfScope prof(kProfTranspose, tbytes, st);
-    FFB_CUDA(launch_transpose(workspace_dev, vec_dev, p->dim_b, p->dim_a, p->dim_a, p->dim_b,
-                              p->dev.sm_count, st));
-  }
-  return FFB_OK;
+  return ffb_apply_orbital_rotation_beta_block(p, vec_dev, p->dim_a, p->dim_b, workspace_dev, stream);
 }
 
 // ---------------------------------------------------------------- _lib-level kernels

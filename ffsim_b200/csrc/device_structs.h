@@ -86,9 +86,14 @@ constexpr int kMaxRunLen = 3;
 FFB_HD constexpr int run_code(int q_hi_rel, int len) { return q_hi_rel * 4 + len; }
 
 struct PassParams {
-  void *data;  // complex128 state (or transposed workspace), updated in place
+  void *data;  // complex128 state (or transposed workspace) the tiles are read from
   long long row_stride;  // element stride between consecutive string addresses
   long long col_stride;  // element stride between consecutive batch columns
+  // where the tiles are written: the same buffer and strides (in place), or -- first / last pass of a
+  // beta-side rotation that works on a transposed copy -- the other layout, which folds the
+  // transposition into the pass (tiles are disjoint, so out of place is as safe as in place)
+  void *out;
+  long long out_row_stride, out_col_stride;
   long long n_cols;      // batch columns
   const void *rowphase;  // complex128[dim] multiplied into every row on store, or NULL
   const uint32_t *u32;

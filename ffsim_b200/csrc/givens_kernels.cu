@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
     {
       long long unit_again = unit;
       asm volatile("" : "+l"(unit_again));  // decode afresh: keep the geometry out of the sub-pass registers
-      double2 *__restrict__ data = reinterpret_cast<double2 *>(p.data);
+      double2 *__restrict__ data = reinterpret_cast<double2 *>(p.out);
       const double2 *__restrict__ rowphase = reinterpret_cast<const double2 *>(p.rowphase);
       const long long local = unit_again - G.unit_begin;
       const long long combo = local / G.n_strips;
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
       const uint32_t rowbase = p.u32[G.combo_base_off + combo];
       const uint32_t *__restrict__ tab = p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
       const int n_el = R * cols;
-      const bool row_major = p.col_stride == 1;
+      const bool row_major = p.out_col_stride == 1;
       for (int e_base = 0; e_base < n_el; e_base += kTilePerThread * nthr) {
         uint32_t grow[kTilePerThread];
 #pragma unroll
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
               if (j < ncv && !FFB_KNOB(2)) {
                 double2 v = tile[j * Rp + r];
                 if (rowphase) v = make_double2(v.x * f[k].x - v.y * f[k].y, v.x * f[k].y + v.y * f[k].x);
-                data[(long long)grow[h * kHalf + k] * p.row_stride + (col0 + j) * p.col_stride] = v;
+                data[(long long)grow[h * kHalf + k] * p.out_row_stride + (col0 + j) * p.out_col_stride] = v;
               }
             }
           }

@@ -435,7 +435,7 @@ int ffb_set_option(const char *key, int64_t value) {
       return fail(FFB_EINVAL, "threads out of range (32.." + std::to_string(FFB_TPB) + ", the CTA size the kernel is built for)");
     g_opt.threads = (int)value;
   } else if (k == "beta_mode") {
-    if (value < 0 || value > 2) return fail(FFB_EINVAL, "beta_mode out of range");
+    if (value < 0 || value > 3) return fail(FFB_EINVAL, "beta_mode out of range");
     g_opt.beta_mode = (int)value;
   } else {
     return fail(FFB_EINVAL, "ffb_set_option: unknown key " + k);

@@ -466,16 +466,14 @@ def _rotate_beta_local(sv: ShardedVector, plan, stream) -> None:
 
     if sv.n_rows == 0:
         return
-    if _lib.lib.ffb_plan_beta_in_place(plan.handle):
-        _lib.check(_lib.lib.ffb_apply_orbital_rotation_strided(
-            plan.handle, 1, sv.local.data_ptr(), sv.n_rows, 1, sv.dim_b, stream))
-        return
-    ws = torch.empty(sv.dim_b * sv.n_rows, dtype=torch.complex128, device=sv.device)
-    _lib.check(_lib.lib.ffb_transpose(sv.local.data_ptr(), ws.data_ptr(), sv.n_rows, sv.dim_b,
-                                      sv.dim_b, sv.n_rows, stream))
-    _lib.check(_lib.lib.ffb_apply_orbital_rotation_rows(plan.handle, 1, ws.data_ptr(), sv.n_rows, sv.n_rows, stream))
-    _lib.check(_lib.lib.ffb_transpose(ws.data_ptr(), sv.local.data_ptr(), sv.dim_b, sv.n_rows,
-                                      sv.n_rows, sv.dim_b, stream))
+    # in place when the beta sector fits one window; otherwise through a transposed copy whose
+    # transpositions the library folds into the first and the last pass
+    ws_ptr = None
+    if not _lib.lib.ffb_plan_beta_in_place(plan.handle):
+        ws = torch.empty(sv.dim_b * sv.n_rows, dtype=torch.complex128, device=sv.device)
+        ws_ptr = ws.data_ptr()
+    _lib.check(_lib.lib.ffb_apply_orbital_rotation_beta_block(
+        plan.handle, sv.local.data_ptr(), sv.n_rows, sv.dim_b, ws_ptr, stream))
 
 
 def _rotate_alpha_local(sv: ShardedVector, plan, stream) -> None:

@@ -111,14 +111,12 @@ class _Runner:
         elif prim.kind == "beta":
             assert (c0, c1) == (0, self.dim_b)
             plan = self.plan_for(prim)
-            if L.ffb_plan_beta_in_place(plan.handle):
-                _lib.check(L.ffb_apply_orbital_rotation_strided(plan.handle, 1, self.ptr(r0, 0), n_rows, 1,
-                                                                self.dim_b, st))
-            else:  # multi-pass beta side: the block goes through a transposed copy [dim_b x n_rows]
+            ws_ptr = None
+            if not L.ffb_plan_beta_in_place(plan.handle):  # multi-pass beta side: transposed copy [dim_b x n_rows]
                 ws = torch.empty(n_rows * self.dim_b, dtype=torch.complex128, device=self.dev.device)
-                _lib.check(L.ffb_transpose(self.ptr(r0, 0), ws.data_ptr(), n_rows, self.dim_b, self.dim_b, n_rows, st))
-                _lib.check(L.ffb_apply_orbital_rotation_rows(plan.handle, 1, ws.data_ptr(), n_rows, n_rows, st))
-                _lib.check(L.ffb_transpose(ws.data_ptr(), self.ptr(r0, 0), self.dim_b, n_rows, n_rows, self.dim_b, st))
+                ws_ptr = ws.data_ptr()
+            _lib.check(L.ffb_apply_orbital_rotation_beta_block(plan.handle, self.ptr(r0, 0), n_rows, self.dim_b,
+                                                               ws_ptr, st))
         elif prim.kind == "diag_coulomb":
             aa, ab, bb = prim.mats
             _lib.check(L.ffb_apply_diag_coulomb_evolution_block(

@@ -153,6 +153,15 @@ int ffb_apply_orbital_rotation_strided(ffb_plan *p, int side, void *data_dev, in
                                        int64_t row_stride, int64_t col_stride, void *stream);
 /* 1 when the plan rotates the beta index in place, 0 when it goes through a transposed copy. */
 int ffb_plan_beta_in_place(const ffb_plan *p);
+/* Beta-side rotations of the plan on a block of n_rows locally held alpha rows (row-major,
+ * n_rows x dim_b, row stride ld): what python/ffsim/gates/orbital_rotation.py:139-150 does with a
+ * transposed view.  In place when ffb_plan_beta_in_place; otherwise through workspace_dev
+ * (n_rows * dim_b elements, laid out dim_b x n_rows).  The transpositions are folded into the first
+ * and the last pass when their windows start at orbital 0 (the tiles of such a pass are contiguous
+ * runs of the beta index, so it can read or write the native layout directly); a separate transpose
+ * kernel runs only where that does not hold (or always with option beta_mode = 3). */
+int ffb_apply_orbital_rotation_beta_block(ffb_plan *p, void *block_dev, int64_t n_rows, int64_t ld,
+                                          void *workspace_dev, void *stream);
 
 /* ------------------------------------------------------ diagonal operators
  * Replaces src/gates/diag_coulomb.rs:21,95 (num / z representation),

@@ -1,8 +1,16 @@
 #!/bin/bash
-# round 2 GPU check: host facts, GPU test-suite, the contract bench at N=1
+# One GPU-box call: the GPU test-suite, then device timings at the bench shapes (developer tool).
+#   scripts/gpu_check.sh <tag> ["<norb> <na> <nb>|<opts>" ...]
+TAG=${1:-chk}; shift
 mkdir -p gpurun_out
-TAG=${1:-r2i}
-{ free -g; nproc; cat /sys/fs/cgroup/memory.max 2>/dev/null; nvidia-smi -L; } > gpurun_out/${TAG}_host.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" >> gpurun_out/${TAG}_bench.err
-tail -3 gpurun_out/${TAG}_pytest.log
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
+tail -4 gpurun_out/${TAG}_pytest.log
+bash scripts/sweep.sh ${TAG}_sweep "$@" > /dev/null 2>&1
+python - <<PY
+import json
+for l in open('gpurun_out/${TAG}_sweep.jsonl'):
+    try: d = json.loads(l)
+    except Exception:
+        print(l.strip()[:300]); continue
+    print(d['opts'] or 'default', '|', d['plan'].split(';')[1][:150], '| both %.2f alpha %.2f beta %.2f' % (d['orbital_rotation_ms'], d['alpha_only_ms'], d['beta_only_ms']))
+PY

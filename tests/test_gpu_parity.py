@@ -112,6 +112,8 @@ def test_orbital_rotation_spinless(norb, nocc):
 @pytest.mark.parametrize("opts", [
     dict(smem_bytes=4096, min_cols=2, sub_window=3),
     dict(smem_bytes=8192, min_cols=4, sub_window=4, beta_mode=2),
+    dict(smem_bytes=8192, min_cols=4, sub_window=4, beta_mode=3),
+    dict(smem_bytes=4096, min_cols=2, sub_window=5, beta_mode=2),
     dict(smem_bytes=16384, min_cols=1, sub_window=5, beta_mode=1),
     dict(smem_bytes=32768, min_cols=4, sub_window=6, threads=256),
     dict(sub_window=2, threads=128),
@@ -128,6 +130,29 @@ def test_orbital_rotation_plan_variants(opts, norb, nelec):
     ua, ub = rand.random_unitary(norb, seed=rng), rand.random_unitary(norb, seed=rng)
     got = ffsim.apply_orbital_rotation(vec, (ua, ub), norb, nelec)
     assert rel_err(got, cref.apply_orbital_rotation(vec, (ua, ub), norb, nelec)) < TOL
+
+
+def test_beta_transposes_fold_into_the_passes():
+    """A multi-pass beta side whose first and last windows start at orbital 0 needs no transpose kernel:
+    two state sweeps fewer than with separate transposes (beta_mode=3), same result."""
+    from ffsim_b200.gates.orbital_rotation import get_plan
+
+    norb, nelec = 12, (5, 6)
+    rng = np.random.default_rng(77)
+    vec = _state(norb, nelec, rng)
+    u = rand.random_unitary(norb, seed=rng)
+    want = cref.apply_orbital_rotation(vec, (None, u), norb, nelec)
+    sweeps = {}
+    for mode in (2, 3):
+        for k, v in dict(smem_bytes=16384, min_cols=2, beta_mode=mode).items():
+            _lib.set_option(k, v)
+        plan = get_plan(norb, nelec, None, u)
+        assert "layout=transposed" in plan.describe() and plan.describe().count("[lo=") >= 2
+        sweeps[mode] = plan.n_state_passes()
+        assert rel_err(ffsim.apply_orbital_rotation(vec, (None, u), norb, nelec), want) < TOL
+    first_lo0 = "transposed [lo=0 " in plan.describe()
+    assert sweeps[3] - sweeps[2] >= (1 if first_lo0 else 0)
+    assert sweeps[3] - sweeps[2] <= 2
 
 
 def test_docs_golden_vectors():
