@@ -26,7 +26,14 @@ from ffsim_b200.gates import (
 )
 from ffsim_b200.hamiltonians import DiagonalCoulombHamiltonian, DoubleFactorizedHamiltonian
 from ffsim_b200.init_cache import init_cache
-from ffsim_b200.pipeline import evolve_host, pinned_empty
+from ffsim_b200.pipeline import (
+    HostEvolution,
+    evolve_host,
+    evolve_host_async,
+    evolve_host_many,
+    pinned_empty,
+    release_device_buffers,
+)
 from ffsim_b200.protocols import apply_unitary, linear_operator
 from ffsim_b200.states import Spin, dim, dims, hartree_fock_state
 from ffsim_b200.trotter import (
@@ -91,7 +98,11 @@ __all__ = [
     "contract_diag_coulomb",
     "contract_num_op_sum",
     "diag_coulomb_linop",
+    "HostEvolution",
     "evolve_host",
+    "evolve_host_async",
+    "evolve_host_many",
+    "release_device_buffers",
     "dim",
     "dims",
     "hartree_fock_state",

@@ -20,7 +20,8 @@
 namespace ffb {
 
 #ifdef FFB_DEBUG_KNOBS
-// what-if timing switches (developer builds only; results are wrong when any is set)
+// what-if timing switches (developer builds only; results are wrong when any is set):
+// 1 no sub-pass barriers, 2 no global traffic, 4 no rotations, 8 no register blocks, 16 no tile store, 32 no tile load
 __device__ int g_debug_knobs = 0;
 #define FFB_KNOB(bit) (g_debug_knobs & (bit))
 #else
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
               r = e - j * R;
             }
             double2 *dst = tile + j * Rp + r;
-            if (j < ncv && !FFB_KNOB(2))
+            if (j < ncv && !FFB_KNOB(2) && !FFB_KNOB(32))
               cp_async16(dst, data + (long long)(rowbase + trow[k]) * p.row_stride + (col0 + j) * p.col_stride);
             else
               *dst = make_double2(0.0, 0.0);
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
                 j = fast_div(e, inv_R);
                 r = e - j * R;
               }
-              if (j < ncv && !FFB_KNOB(2)) {
+              if (j < ncv && !FFB_KNOB(2) && !FFB_KNOB(16)) {
                 double2 v = tile[j * Rp + r];
                 if (rowphase) v = make_double2(v.x * f[k].x - v.y * f[k].y, v.x * f[k].y + v.y * f[k].x);
                 data[(long long)grow[h * kHalf + k] * p.out_row_stride + (col0 + j) * p.out_col_stride] = v;

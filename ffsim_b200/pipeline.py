@@ -133,8 +133,55 @@ def _copy2d(dst: int, dst_pitch: int, src: int, src_pitch: int, width: int, heig
     _lib.check(_lib.lib.ffb_memcpy2d_async(dst, dst_pitch, src, src_pitch, width, height, kind, stream))
 
 
-def evolve_host(vec, steps, norb: int, nelec: tuple[int, int], *, n_chunks: int | None = None) -> np.ndarray:
-    """Apply ``steps`` to the host vector ``vec`` and return the result as a new (page-locked) NumPy array.
+class _Lane:
+    """Per-device resources of the host pipeline: the two copy streams (one per PCIe direction) and a ring of
+    device buffers, so that consecutive applications overlap -- the upload of the next state runs while the
+    previous one is still being computed and downloaded."""
+
+    def __init__(self, dev_index: int):
+        self.dev_index = dev_index
+        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self.ring: dict[int, list] = {}  # n_complex -> [[tensor, event recorded after the last copy out of it], ...]
+        self.turn: dict[int, int] = {}
+
+    def acquire(self, n: int, depth: int):
+        ring = self.ring.setdefault(n, [])
+        if len(ring) < depth:
+            ring.append([torch.empty(n, dtype=torch.complex128, device="cuda"), None])
+            slot = ring[-1]
+        else:
+            k = self.turn.get(n, 0) % len(ring)
+            self.turn[n] = k + 1
+            slot = ring[k]
+        return slot
+
+    def trim(self, keep_n: int) -> None:
+        for n in [n for n in self.ring if n != keep_n]:
+            del self.ring[n]
+
+
+_LANES: dict[int, _Lane] = {}
+_DEPTH = 2  # device buffers per state size: one being filled while the other is computed on / drained
+
+
+class HostEvolution:
+    """Handle of an application started by :func:`evolve_host_async`; ``result()`` waits for the download."""
+
+    def __init__(self, out: np.ndarray, done: "torch.cuda.Event | None", keep):
+        self._out, self._done, self._keep = out, done, keep
+
+    def done(self) -> bool:
+        return self._done is None or self._done.query()
+
+    def result(self) -> np.ndarray:
+        if self._done is not None:
+            self._done.synchronize()
+            self._done, self._keep = None, None
+        return self._out
+
+
+def evolve_host_async(vec, steps, norb: int, nelec: tuple[int, int], *, n_chunks: int | None = None) -> HostEvolution:
+    """Start applying ``steps`` to the host vector ``vec``; returns at once with a :class:`HostEvolution`.
 
     ``steps`` is a list of tuples, applied in order:
 
@@ -142,8 +189,12 @@ def evolve_host(vec, steps, norb: int, nelec: tuple[int, int], *, n_chunks: int 
     * ``("diag_coulomb", mat, time[, z_representation])``   -- as ``apply_diag_coulomb_evolution``
     * ``("num_op_sum", coeffs, time)``                      -- as ``apply_num_op_sum_evolution``
 
-    The input is not modified.  ``n_chunks`` (default: one per ~64 MB, at most 16) is the number of column
-    strips / row blocks the copies are cut into.
+    The input is not modified, but it must stay untouched until ``result()`` has returned (it is read by
+    asynchronous copies; pageable memory makes them synchronous).  ``n_chunks`` (default: one per ~64 MB, at
+    most 16) is the number of column strips / row blocks the copies are cut into.  Applications started back
+    to back overlap: uploads, kernels and downloads each run in order on their own stream, and the device
+    state buffers form a ring of two, so the upload of one application proceeds while the previous one is
+    computed and sent back (both PCIe directions busy at once).
     """
     _device.require_cuda()
     nelec = (int(nelec[0]), int(nelec[1]))
@@ -153,7 +204,7 @@ def evolve_host(vec, steps, norb: int, nelec: tuple[int, int], *, n_chunks: int 
     if host.size != dim_a * dim_b:
         raise ValueError(f"vec has {host.size} entries, expected {dim_a * dim_b} for norb={norb}, nelec={nelec}")
     if host.size == 0:
-        return host.copy()
+        return HostEvolution(host.copy(), None, None)
     dev_index = _device.sync_device()
     prims = _expand(steps, norb, nelec)
     nbytes = 16 * host.size
@@ -171,11 +222,21 @@ def evolve_host(vec, steps, norb: int, nelec: tuple[int, int], *, n_chunks: int 
     head, middle, tail = prims[:n_head], prims[n_head : len(prims) - n_tail], prims[len(prims) - n_tail :]
 
     with torch.cuda.device(dev_index):
-        dev = torch.empty(host.size, dtype=torch.complex128, device="cuda")
-        out = pinned_empty(host.size)
+        lane = _LANES.get(dev_index)
+        if lane is None:
+            lane = _LANES[dev_index] = _Lane(dev_index)
+        lane.trim(host.size)  # one state size at a time keeps its ring; other sizes give their memory back
         main = torch.cuda.current_stream()
-        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-        s_in.wait_stream(main)  # the allocation above is ordered on the current stream
+        s_in, s_out = lane.s_in, lane.s_out
+        slot = lane.acquire(host.size, _DEPTH)
+        dev = slot[0]
+        dev.record_stream(s_in)  # the caching allocator must not hand the buffer on while copies are pending
+        dev.record_stream(s_out)
+        if slot[1] is not None:
+            s_in.wait_event(slot[1])  # the previous user of this buffer has been copied out
+        else:
+            s_in.wait_stream(main)  # a fresh allocation is ordered on the current stream
+        out = pinned_empty(host.size)
         run = _Runner(dev, norb, nelec, main.cuda_stream)
         src, dst, pitch = host.ctypes.data, out.ctypes.data, 16 * dim_b
         everything_in_head = not middle and not tail
@@ -214,7 +275,36 @@ def evolve_host(vec, steps, norb: int, nelec: tuple[int, int], *, n_chunks: int 
                 s_out.wait_event(done)
                 _copy2d(dst + 16 * r0 * dim_b, pitch, run.ptr(r0, 0), pitch, 16 * (r1 - r0) * dim_b, 1, _D2H,
                         s_out.cuda_stream)
-        s_out.synchronize()
-        main.wait_stream(s_out)  # `dev` may be reused by the allocator only after the copies out of it
-        main.synchronize()
-    return out
+        finished = torch.cuda.Event()
+        finished.record(s_out)
+        slot[1] = finished
+    return HostEvolution(out, finished, (host, dev))
+
+
+def evolve_host(vec, steps, norb: int, nelec: tuple[int, int], *, n_chunks: int | None = None) -> np.ndarray:
+    """Apply ``steps`` (see :func:`evolve_host_async`) to the host vector ``vec`` and return the result as a
+    new (page-locked) NumPy array.  The input is not modified."""
+    return evolve_host_async(vec, steps, norb, nelec, n_chunks=n_chunks).result()
+
+
+def evolve_host_many(vecs, steps, norb: int, nelec: tuple[int, int], *, n_chunks: int | None = None) -> list[np.ndarray]:
+    """``[evolve_host(v, steps, ...) for v in vecs]`` with consecutive applications overlapped: while one
+    state is computed and downloaded, the next one is already being uploaded (see :func:`evolve_host_async`).
+    At most two applications are in flight (two device state buffers); results come back in order."""
+    results: list[np.ndarray] = []
+    pending: list[HostEvolution] = []
+    for v in vecs:
+        if len(pending) >= _DEPTH:  # its device buffer is the one the next application needs
+            results.append(pending.pop(0).result())
+        pending.append(evolve_host_async(v, steps, norb, nelec, n_chunks=n_chunks))
+    results.extend(h.result() for h in pending)
+    return results
+
+
+def release_device_buffers() -> None:
+    """Free the device state buffers the host pipeline keeps between calls."""
+    torch.cuda.synchronize()
+    for lane in _LANES.values():
+        lane.ring.clear()
+        lane.turn.clear()
+    torch.cuda.empty_cache()

@@ -1,6 +1,7 @@
 """What-if timing with the developer build (scripts/build_dbg.sh): which phase of the fused
 kernel costs what.  knobs: 1 = no sub-pass barriers, 2 = no global load/store, 4 = no rotation
-math, 8 = no register-block processing at all."""
+math, 8 = no register-block processing at all, 16 = no tile store, 32 = no tile load.
+env: FFB_KNOBS=0,8,24 (knob sets to time), FFB_SIDE=beta."""
 import ctypes
 import json
 import os
@@ -23,14 +24,16 @@ _lib.lib.ffb_debug_knobs.argtypes = [ctypes.c_int]
 u = ffsim.random.random_unitary(norb, seed=1)
 vec = torch.randn(ffsim.dim(norb, nelec), dtype=torch.complex128, device="cuda")
 res = {}
-for knobs in (0, 2, 4, 8, 6, 10):
+KNOBS = [int(k) for k in os.environ.get("FFB_KNOBS", "0,2,4,8,6,10").split(",")]
+SIDE = (None, u) if os.environ.get("FFB_SIDE") == "beta" else (u, None)
+for knobs in KNOBS:
     _lib.lib.ffb_debug_knobs(knobs)
     ts = []
     for it in range(6):
         vec.normal_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        ffsim.apply_orbital_rotation(vec, (u, None), norb, nelec, copy=False)
+        ffsim.apply_orbital_rotation(vec, SIDE, norb, nelec, copy=False)
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))

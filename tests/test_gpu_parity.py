@@ -534,6 +534,43 @@ def test_evolve_host_matches_sequential_calls(opts, n_chunks):
         ffsim.evolve_host(vec[:-1], [("orbital_rotation", u1)], norb, nelec)
 
 
+@pytest.mark.parametrize("opts", [{}, {"smem_bytes": 16 * 1024, "beta_mode": 2}])
+def test_evolve_host_async_overlapped_applications(opts):
+    """Applications started back to back (ffsim_b200.evolve_host_async / evolve_host_many: ring of two device
+    buffers, uploads of one application under the kernels and downloads of the one before) give, each, what
+    a lone evolve_host call gives -- different states, different sizes in between, inputs untouched."""
+    for k, v in opts.items():
+        _lib.set_option(k, v)
+    norb, nelec = 10, (4, 5)
+    rng = np.random.default_rng(2020)
+    u = rand.random_unitary(norb, seed=rng)
+    mat = rand.random_real_symmetric_matrix(norb, seed=rng)
+    steps = [("orbital_rotation", u), ("diag_coulomb", mat, 0.25)]
+    vecs = []
+    for _ in range(7):
+        pinned = ffsim.pinned_empty(ffsim.dim(norb, nelec))
+        pinned[:] = _state(norb, nelec, rng)
+        vecs.append(pinned)
+    want = [ffsim.apply_diag_coulomb_evolution(ffsim.apply_orbital_rotation(v, u, norb, nelec), mat, 0.25, norb, nelec)
+            for v in vecs]
+    before = [v.copy() for v in vecs]
+    got = ffsim.evolve_host_many(vecs, steps, norb, nelec, n_chunks=3)
+    assert len(got) == len(vecs)
+    for g, w, v, b in zip(got, want, vecs, before):
+        assert rel_err(g, w) <= TOL
+        assert np.array_equal(v, b)
+    # handles: results may be collected in any order; a different state size in between re-sizes the ring
+    handles = [ffsim.evolve_host_async(v, steps, norb, nelec, n_chunks=2) for v in vecs[:4]]
+    small = _state(6, (3, 3), rng)
+    u6 = rand.random_unitary(6, seed=rng)
+    h_small = ffsim.evolve_host_async(small, [("orbital_rotation", u6)], 6, (3, 3))
+    assert rel_err(h_small.result(), ffsim.apply_orbital_rotation(small, u6, 6, (3, 3))) <= TOL
+    for k in (3, 0, 2, 1):
+        assert rel_err(handles[k].result(), want[k]) <= TOL
+        assert handles[k].done()
+    ffsim.release_device_buffers()
+
+
 # ------------------------------------------------------------------ BASELINE shapes: properties
 
 def test_c2_shape_against_c_oracle_and_properties():
