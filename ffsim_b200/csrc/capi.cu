@@ -333,6 +333,11 @@ int apply_side(ffb_plan *plan, int which, void *data, int64_t n_cols, int64_t ro
       P.out_col_stride = alt.col_stride;
     }
     P.n_cols = n_cols;
+    // a tile column is one contiguous run of memory when consecutive strings are adjacent and the window
+    // starts at orbital 0 (tile row r is then string rowbase + r): those columns move as bulk copies
+    const bool runs = plan->opt.bulk_copies != 0 && dp.sched.lo == 0;
+    P.bulk_in = runs && P.row_stride == 1 && reinterpret_cast<uintptr_t>(P.data) % 16 == 0;
+    P.bulk_out = runs && P.out_row_stride == 1 && reinterpret_cast<uintptr_t>(P.out) % 16 == 0;
     P.rowphase = (last && sp.has_phases) ? sp.d_rowphase : nullptr;
     P.u32 = dp.d_u32;
     P.u8 = dp.d_u8;

@@ -94,6 +94,10 @@ struct PassParams {
   // transposition into the pass (tiles are disjoint, so out of place is as safe as in place)
   void *out;
   long long out_row_stride, out_col_stride;
+  // 1 when a tile column is ONE contiguous run of the buffer it is read from / written to (string
+  // stride 1 and a window that starts at orbital 0, so tile row r is string rowbase + r): such a column
+  // moves as a single bulk copy of the TMA unit (cp.async.bulk + mbarrier) instead of R 16-byte copies
+  int bulk_in, bulk_out;
   long long n_cols;      // batch columns
   const void *rowphase;  // complex128[dim] multiplied into every row on store, or NULL
   const uint32_t *u32;

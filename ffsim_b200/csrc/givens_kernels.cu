@@ -284,6 +284,53 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// ---------------------------------------------------------------- bulk (TMA) copies and mbarrier
+// A tile column that is one contiguous run of global memory (see PassParams::bulk_in / bulk_out) is
+// moved by the copy engine of the SM: one cp.async.bulk per column, completion of the loads signalled
+// on an mbarrier through its transaction count, the stores tracked as a bulk group.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// generic-proxy accesses of shared memory before / after accesses of the same bytes by the bulk copies
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes,
+                                          unsigned long long *bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gmem_src), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(s), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_and_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // n / d for n * d < 2^32 with a precomputed inv = 0xFFFFFFFF / d + 1 (which wraps to 0 for d == 1)
 __device__ __forceinline__ int fast_div(int n, unsigned inv) {
   return inv ? (int)__umulhi((unsigned)n, inv) : n;
@@ -349,6 +396,15 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  __shared__ __align__(8) unsigned long long tile_bar;  // completion of a tile's bulk loads
+  unsigned tile_phase = 0;
+  if (p.bulk_in) {
+    if (tid == 0) {
+      mbar_init(&tile_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
 #ifdef FFB_DEBUG_TIMING
   if (tid < 32 * 8) s_phase_cycles[tid >> 3][tid & 7] = 0;
   __syncthreads();
@@ -383,6 +439,20 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
       const uint32_t *__restrict__ tab = p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
       const int n_el = R * cols;
       const bool row_major = p.col_stride == 1;  // batch index contiguous in memory
+      if (p.bulk_in && !FFB_KNOB(2) && !FFB_KNOB(32)) {
+        // a column of the tile is the contiguous run [rowbase, rowbase + R) of its batch column: one bulk
+        // copy each, issued by the first ncv threads; thread 0 posts the byte count the barrier waits for
+        // (the previous tile's shared-memory reads were generic: order them before the copy engine's writes)
+        fence_proxy_async();
+        if (tid == 0) mbar_expect_tx(&tile_bar, (unsigned)(ncv * R * (int)sizeof(double2)));
+        if (tid < ncv)
+          bulk_load(tile + tid * Rp, data + (long long)rowbase + (col0 + tid) * p.col_stride,
+                    (unsigned)(R * (int)sizeof(double2)), &tile_bar);
+        for (int e = ncv * R + tid; e < n_el; e += nthr) {  // columns past the edge of the batch
+          const int j = fast_div(e, inv_R);
+          tile[j * Rp + (e - j * R)] = make_double2(0.0, 0.0);
+        }
+      } else
       // Each element needs its row offset from the (global) tile row table first.  All table loads
       // of a thread (a 220 KB tile is <= 28 elements per thread at 512 threads) are issued before the
       // first copy, and the copies are asynchronous (LDGSTS): the whole tile costs two memory
@@ -477,6 +547,10 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
       }
     }
     cp_async_wait_all();  // the tile, the first offset table and the first block list
+    if (p.bulk_in && !FFB_KNOB(2) && !FFB_KNOB(32)) {
+      mbar_wait(&tile_bar, tile_phase);
+      tile_phase ^= 1u;
+    }
     __syncthreads();
     FFB_TACC(1);
     cached_group = work ? gi : cached_group;
@@ -556,6 +630,23 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
       const uint32_t *__restrict__ tab = p.u32 + G.tabrow_off + (size_t)p.u8[G.combo_low_off + combo] * R;
       const int n_el = R * cols;
       const bool row_major = p.out_col_stride == 1;
+      if (p.bulk_out && !FFB_KNOB(2) && !FFB_KNOB(16)) {
+        // every column goes out as one bulk copy; the per-row phases are multiplied in place first
+        if (rowphase) {
+          for (int e = tid; e < ncv * R; e += nthr) {
+            const int j = fast_div(e, inv_R), r = e - j * R;
+            const double2 v = tile[j * Rp + r], f = rowphase[rowbase + r];
+            tile[j * Rp + r] = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+          }
+        }
+        fence_proxy_async();  // this thread's writes of the tile (sub-passes, phases) before the copy engine reads it
+        __syncthreads();
+        if (tid < ncv) {
+          bulk_store(data + (long long)rowbase + (col0 + tid) * p.out_col_stride, tile + tid * Rp,
+                     (unsigned)(R * (int)sizeof(double2)));
+          bulk_store_commit_and_wait_read();  // the tile may be overwritten once the engine has read it
+        }
+      } else
       for (int e_base = 0; e_base < n_el; e_base += kTilePerThread * nthr) {
         uint32_t grow[kTilePerThread];
 #pragma unroll
@@ -604,6 +695,7 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
     if (tid == 0) s_tl_on = 0;  // only the CTA's first tile is logged
 #endif
   }
+  if (p.bulk_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this thread's bulk stores have landed
 #ifdef FFB_DEBUG_TIMING
   __syncthreads();
   if (tid < nwarp * 8) atomicAdd(&g_phase_cycles[tid & 7], s_phase_cycles[tid >> 3][tid & 7]);

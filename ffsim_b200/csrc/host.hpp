@@ -68,6 +68,7 @@ struct PlanOptions {
   int max_cols;        // widest column strip of a full-height tile
   int sub_window;      // register block width (2..6)
   int threads;         // CTA size of the fused pass kernel
+  int bulk_copies;     // 1: contiguous tile columns move as TMA bulk copies (cp.async.bulk + mbarrier), 0: 16-byte copies
   int beta_mode;       // 0 auto, 1 native strided, 2 transposed copy (transpositions folded into the first / last
                        // pass where possible), 3 transposed copy with separate transpose kernels
 };

@@ -20,7 +20,7 @@ namespace ffb {
 
 namespace {
 PlanOptions g_opt = {/*smem_bytes=*/220 * 1024, /*min_cols=*/3, /*max_cols=*/8,
-                     /*sub_window=*/6,          /*threads=*/512, /*beta_mode=*/0};
+                     /*sub_window=*/6,          /*threads=*/512, /*bulk_copies=*/1, /*beta_mode=*/0};
 std::mutex g_opt_mu;
 }  // namespace
 
@@ -434,6 +434,9 @@ int ffb_set_option(const char *key, int64_t value) {
     if (value < 32 || value > FFB_TPB || value % 32)
       return fail(FFB_EINVAL, "threads out of range (32.." + std::to_string(FFB_TPB) + ", the CTA size the kernel is built for)");
     g_opt.threads = (int)value;
+  } else if (k == "bulk_copies") {
+    if (value < 0 || value > 1) return fail(FFB_EINVAL, "bulk_copies out of range");
+    g_opt.bulk_copies = (int)value;
   } else if (k == "beta_mode") {
     if (value < 0 || value > 3) return fail(FFB_EINVAL, "beta_mode out of range");
     g_opt.beta_mode = (int)value;
@@ -452,6 +455,7 @@ int64_t ffb_get_option(const char *key) {
   if (k == "max_cols") return g_opt.max_cols;
   if (k == "sub_window") return g_opt.sub_window;
   if (k == "threads") return g_opt.threads;
+  if (k == "bulk_copies") return g_opt.bulk_copies;
   if (k == "beta_mode") return g_opt.beta_mode;
   return -1;
 }

@@ -80,7 +80,7 @@ def get_plan(norb: int, nelec: tuple[int, int], mat_a, mat_b) -> _Plan:
 
     key = (dev, norb, n_alpha, n_beta, sig(decomp_a), sig(decomp_b),
            tuple(_lib.get_option(k) for k in ("smem_bytes", "min_cols", "max_cols", "sub_window",
-                                              "threads", "beta_mode")))
+                                              "threads", "beta_mode", "bulk_copies")))
     ra, na, pa = _side_args(decomp_a)
     rb, nb, pb = _side_args(decomp_b)
     plan = _PLAN_CACHE.get(key)

@@ -36,7 +36,7 @@ def rel_err(got, want):
 
 @pytest.fixture(autouse=True)
 def _default_options():
-    saved = {k: _lib.get_option(k) for k in ("smem_bytes", "min_cols", "max_cols", "sub_window", "threads", "beta_mode")}
+    saved = {k: _lib.get_option(k) for k in ("smem_bytes", "min_cols", "max_cols", "sub_window", "threads", "beta_mode", "bulk_copies")}
     yield
     for k, v in saved.items():
         _lib.set_option(k, v)
