@@ -525,10 +525,17 @@ def main():
     ap.add_argument("--config", type=str, default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-c2", action="store_true", help="skip the second (configs[1]) record at N=1")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: whatever libraries print on file descriptor 1 meanwhile (NCCL
+    # announces its version there) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
