@@ -57,6 +57,14 @@ FFB_HD constexpr int tile_col_stride(int R, int cols) {
   const int want = (cols & 1) ? (cols & 7) : (cols == 2 ? 4 : (cols == 4 ? 2 : 1));
   return R + ((want - R) & 7);
 }
+// Order of the (block, column) items of a class inside its 32-item chunks.  With the column index
+// fastest a quarter-warp (one shared-memory wavefront of 16-byte accesses) holds the same block in
+// several tile columns -- which the column stride already places in different bank groups -- and only
+// 8 / cols different blocks, so it needs far fewer blocks with distinct starting rows modulo 8 than
+// with the block index fastest.  That works out for an odd column count, for 2 and 4, and for multiples
+// of 8 (tile_col_stride); other even counts keep the block index fastest.
+FFB_HD constexpr bool items_column_fastest(int cols) { return (cols & 1) || cols == 2 || cols == 4 || (cols & 7) == 0; }
+
 struct GroupLaunch {
   int R;                    // tile rows
   int Rp;                   // column stride of the tile, tile_col_stride(R, cols)

@@ -345,11 +345,11 @@ struct ChunkWork {
 
 // The g-th chunk of the concatenated (heavy classes first) chunk list of a sub-pass.  `cend` is the
 // sub-pass's row of the chunk-prefix table: cend[k] = chunks in segments 0..k (0xFFFF past the last
-// segment), cend[kChunkRow-1] = total.  Items of a segment are (column, block) pairs with the block
-// index running fastest: the lanes of a chunk read consecutive block bases.  Everything comes from
+// segment), cend[kChunkRow-1] = total.  Items of a segment are (column, block) pairs, ordered as
+// items_column_fastest() says.  Everything comes from
 // shared memory (the block list of the sub-pass is staged there one sub-pass ahead).
 __device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const uint16_t *cend,
-                                                 const uint32_t *blk, int g, int lane, int cols) {
+                                                 const uint32_t *blk, int g, int lane, int cols, unsigned inv_cols) {
   ChunkWork w;
   w.entry = 0;
   w.mp = 0;
@@ -367,10 +367,19 @@ __device__ __forceinline__ ChunkWork fetch_chunk(const GroupSubDev &gs, const ui
   const int item = ((g - base) << 5) + lane;
   const int count = (int)sq.z;
   if (item < count * cols) {
-    const int col = fast_div(item, sq.w);
+    // (column, block) of the item: the column index runs fastest where that keeps a quarter-warp's
+    // rows in different bank groups (items_column_fastest), else the block index
+    int col, b;
+    if (items_column_fastest(cols)) {
+      b = fast_div(item, inv_cols);
+      col = item - b * cols;
+    } else {
+      col = fast_div(item, sq.w);
+      b = item - col * count;
+    }
     w.col = col;
     w.mp = (int)sq.x;
-    w.entry = blk[(int)sq.y + item - col * count];
+    w.entry = blk[(int)sq.y + b];
   }
   return w;
 }
@@ -587,14 +596,14 @@ __global__ void __launch_bounds__(FFB_TPB, 1)
           return k * nwarp + ((k & 1) ? nwarp - 1 - warp : warp);
         };
         int g = chunk_at(0);
-        ChunkWork cur = fetch_chunk(gs, cend, blk, g, lane, cols);
+        ChunkWork cur = fetch_chunk(gs, cend, blk, g, lane, cols, G.inv_cols);
         for (int k = 1; g < n_chunks; ++k) {
           const int g_next = chunk_at(k);
           ChunkWork nxt;
           nxt.entry = 0;
           nxt.mp = 0;
           nxt.col = 0;
-          if (g_next < n_chunks) nxt = fetch_chunk(gs, cend, blk, g_next, lane, cols);
+          if (g_next < n_chunks) nxt = fetch_chunk(gs, cend, blk, g_next, lane, cols, G.inv_cols);
           FFB_TACC(2);
           if (cur.mp && !FFB_KNOB(8)) {
             const unsigned a_addr = tile_sa + ((unsigned)(cur.col * Rp + (int)(cur.entry & 0xFFFFFFu)) << 4);

@@ -296,8 +296,14 @@ extern "C" int ffb_hostcheck_apply_side_device(int norb, int nocc, const ffb_giv
                 for (int lane = 0; lane < 32; ++lane) {
                   const int item = ((g - base) << 5) + lane;
                   if (item >= count * cols) continue;
-                  const int col = fast_div_host(item, sq.inv_count);
-                  const int b = item - col * count;
+                  int col, b;
+                  if (items_column_fastest(cols)) {
+                    b = fast_div_host(item, 0xFFFFFFFFu / (unsigned)cols + 1u);
+                    col = item - b * cols;
+                  } else {
+                    col = fast_div_host(item, sq.inv_count);
+                    b = item - col * count;
+                  }
                   if (col < 0 || col >= cols || b < 0 || b >= count || sq.begin + b >= gs.n_blocks) return -203;
                   const uint32_t entry = blk[sq.begin + b];
                   // process_item: byte addresses relative to the tile
@@ -335,4 +341,63 @@ extern "C" int ffb_hostcheck_apply_side_device(int norb, int nocc, const ffb_giv
   return 0;
 } catch (const std::exception &) {
   return -200;  // a plan-builder invariant fired (plan.cpp require())
+}
+
+// Shared-memory wavefronts of the register-block gathers (= scatters) of one tile of every group, walked
+// the way the kernel walks them: 32-item chunks of (column, block) pairs with the block index fastest,
+// a quarter-warp (8 lanes, 16-byte accesses) per wavefront when its rows fall in eight different bank
+// groups, more when they collide.  out[0] = wavefronts, out[1] = the conflict-free count, per tile and
+// summed over the groups weighted by their number of tiles per column strip (combinations).
+extern "C" int ffb_hostcheck_gather_wavefronts(int norb, int nocc, const int *q, int n, int cols_req, int col_fast, int64_t *out) try {
+  PlanOptions opt = current_options();
+  std::vector<int> qq(q, q + n);
+  SideSchedule sched = build_schedule(norb, nocc, qq, opt);
+  int64_t actual = 0, ideal = 0;
+  for (const PassSchedule &ps : sched.passes) {
+    PassTablesHost T = build_pass_tables(norb, nocc, ps);
+    std::vector<int> group_R;
+    std::vector<int64_t> group_combos;
+    for (const PassGroupHost &G : T.groups) {
+      group_R.push_back(G.R);
+      group_combos.push_back((int64_t)G.combo_base.size());
+    }
+    DevicePassTables D = pack_device_tables(ps, T);
+    for (size_t gi = 0; gi < group_R.size(); ++gi) {
+      const int R = group_R[gi];
+      const int cols = cols_req > 0 ? cols_req : (int)std::max<int64_t>(1, std::min<int64_t>(8, (opt.smem_bytes / 16) / (R + 7)));
+      const int Rp = tile_col_stride(R, cols);
+      for (size_t s = 0; s < ps.subs.size(); ++s) {
+        const GroupSubDev &gs = D.gsub[D.goff[gi].gsub_off + s];
+        const uint32_t *blk = D.u32.data() + gs.blocks_off;
+        const uint32_t *offtab = D.off32.data() + s * kMaxLowDev * kOffRowDev;
+        for (int sg = 0; sg < gs.n_seg && sg < kMaxSeg; ++sg) {
+          const SegDev &sq = gs.seg[sg];
+          const int mp = sq.mp & 0xFF, count = sq.count;
+          const int nt = (int)binom(ps.subs[s].w, mp);
+          const int items = count * cols;
+          for (int i0 = 0; i0 < items; i0 += 8) {
+            for (int t = 0; t < nt; ++t) {
+              int hits[8] = {0, 0, 0, 0, 0, 0, 0, 0}, worst = 0;
+              for (int l = 0; l < 8 && i0 + l < items; ++l) {
+                const int item = i0 + l;
+                const bool cf = col_fast && items_column_fastest(cols);
+                const int col = cf ? item % cols : item / count, b = cf ? item / cols : item - col * count;
+                const uint32_t entry = blk[sq.begin + b];
+                const uint32_t byte = ((uint32_t)(col * Rp + (int)(entry & 0xFFFFFFu)) << 4) +
+                                      offtab[(entry >> 24) * kOffRowDev + dev_class_offset(ps.subs[s].w, mp) + t];
+                worst = std::max(worst, ++hits[(byte >> 4) & 7]);
+              }
+              actual += worst * group_combos[gi];
+              ideal += group_combos[gi];
+            }
+          }
+        }
+      }
+    }
+  }
+  out[0] = actual;
+  out[1] = ideal;
+  return 0;
+} catch (const std::exception &) {
+  return -200;
 }
