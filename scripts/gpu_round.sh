@@ -2,7 +2,7 @@
 # One GPU-box call (1 GPU): parity tests, smoke, both bench arms, ncu launch lists and full ncu captures of the
 # top kernels at both bench configurations (c3 = norb 18 (7,7), 16.2 GB; c2 = norb 16 (5,5), 305 MB).
 set -u
-TAG=${1:-r2}
+TAG=${1:-r2f}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/${TAG}_gpu.txt; nproc >> gpurun_out/${TAG}_gpu.txt; free -g >> gpurun_out/${TAG}_gpu.txt
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_gpu.log
