@@ -1,6 +1,7 @@
 """Target for compute-sanitizer (memcheck / racecheck / synccheck): every kernel of the library on small
 shapes -- the fused pass kernel with every register-block width (2..6), single- and multi-pass plans,
-native and transposed beta side; the diagonal kernels (evolution, contraction, z representation), the
+native and transposed beta side (transpositions folded into the passes or separate, bulk copies on and off),
+the host pipeline; the diagonal kernels (evolution, contraction, z representation), the
 controlled phase, the _lib-level single-rotation kernels, transpose, vdot, axpby, block copies."""
 import os
 import sys
@@ -21,7 +22,9 @@ for norb, nelec in [(4, (2, 2)), (6, (3, 2)), (8, (4, 4)), (9, (3, 5)), (10, (5,
     ua, ub = ffsim.random.random_unitary(norb, seed=rng), ffsim.random.random_unitary(norb, seed=rng)
     mat = ffsim.random.random_real_symmetric_matrix(norb, seed=rng)
     for opts in [{}, {"sub_window": 2}, {"sub_window": 3}, {"sub_window": 4}, {"sub_window": 5},
-                 {"smem_bytes": 4096, "min_cols": 2}, {"smem_bytes": 8192, "beta_mode": 2}, {"beta_mode": 1, "smem_bytes": 16384},
+                 {"smem_bytes": 4096, "min_cols": 2}, {"smem_bytes": 8192, "beta_mode": 2}, {"smem_bytes": 8192, "beta_mode": 3},
+                 {"smem_bytes": 4096, "min_cols": 2, "sub_window": 5, "beta_mode": 2, "bulk_copies": 0}, {"bulk_copies": 0},
+                 {"beta_mode": 1, "smem_bytes": 16384},
                  {"threads": 128}]:
         saved = {k: _lib.get_option(k) for k in opts}
         for k, v in opts.items():
@@ -41,6 +44,10 @@ for norb, nelec in [(4, (2, 2)), (6, (3, 2)), (8, (4, 4)), (9, (3, 5)), (10, (5,
     ffsim.apply_fsim_gate(vec, 0.3, 0.2, (1, 2), norb, nelec)
     if norb <= 6:
         apply_orbital_rotation_unfused(vec, (ua, ub), norb, nelec)
+    if norb in (6, 9):  # host pipeline: strips in, blocks out, two applications in flight
+        outs = ffsim.evolve_host_many([vec, vec, vec], [("orbital_rotation", (ua, ub)), ("diag_coulomb", mat, 0.2)],
+                                      norb, nelec, n_chunks=2)
+        assert all(abs(np.linalg.norm(o) - 1) < 1e-10 for o in outs)
     ham = ffsim.random.random_diagonal_coulomb_hamiltonian(norb, seed=rng)
     lin = ffsim.linear_operator(ham, norb=norb, nelec=nelec)
     hv = lin @ vec
