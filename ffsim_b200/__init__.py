@@ -31,6 +31,7 @@ from ffsim_b200.pipeline import (
     evolve_host,
     evolve_host_async,
     evolve_host_many,
+    evolve_host_rows_async,
     pinned_empty,
     release_device_buffers,
 )
@@ -102,6 +103,7 @@ __all__ = [
     "evolve_host",
     "evolve_host_async",
     "evolve_host_many",
+    "evolve_host_rows_async",
     "release_device_buffers",
     "dim",
     "dims",

@@ -301,6 +301,64 @@ def evolve_host_many(vecs, steps, norb: int, nelec: tuple[int, int], *, n_chunks
     return results
 
 
+def evolve_host_rows_async(rows, steps, norb: int, nelec: tuple[int, int], *, group=None) -> HostEvolution:
+    """The sharded counterpart of :func:`evolve_host_async` (one process per GPU, ``torch.distributed``
+    initialised): ``rows`` is THIS rank's block of alpha rows of the host state (``ShardedVector`` row
+    distribution, ``(n_rows, dim_b)`` complex128, page-locked for the copies to be asynchronous); the handle's
+    ``result()`` is the same block of the evolved state.  Collective: every rank calls it with the same
+    ``steps``.  The shard is uploaded on its own stream, the operations run on the current stream through the
+    public functions on a ``ShardedVector`` (exchanges over NVLink included), and the result is downloaded on a
+    third stream -- so with two applications in flight the upload of one overlaps the kernels and the
+    download of the one before, and both PCIe directions stay busy."""
+    from ffsim_b200 import apply_diag_coulomb_evolution, apply_num_op_sum_evolution, apply_orbital_rotation
+    from ffsim_b200.distributed import ROWS, ShardedVector
+
+    _device.require_cuda()
+    nelec = (int(nelec[0]), int(nelec[1]))
+    host = np.ascontiguousarray(np.asarray(rows).reshape(-1), dtype=np.complex128)
+    dev_index = _device.sync_device()
+    with torch.cuda.device(dev_index):
+        lane = _LANES.get(dev_index)
+        if lane is None:
+            lane = _LANES[dev_index] = _Lane(dev_index)
+        main = torch.cuda.current_stream()
+        local = torch.empty(host.size, dtype=torch.complex128, device="cuda")
+        sv = ShardedVector(local, norb, nelec, group)  # checks the shard size
+        out = pinned_empty(host.size)
+        if host.size:
+            lane.s_in.wait_stream(main)  # the allocation is ordered on the current stream
+            local.record_stream(lane.s_in)
+            _copy2d(local.data_ptr(), 16 * host.size, host.ctypes.data, 16 * host.size, 16 * host.size, 1, _H2D,
+                    lane.s_in.cuda_stream)
+            arrived = torch.cuda.Event()
+            arrived.record(lane.s_in)
+            main.wait_event(arrived)
+        for step in steps:
+            name = step[0]
+            if name == "orbital_rotation":
+                apply_orbital_rotation(sv, step[1], norb, nelec, copy=False)
+            elif name == "diag_coulomb":
+                apply_diag_coulomb_evolution(sv, step[1], float(step[2]), norb, nelec,
+                                             z_representation=bool(step[3]) if len(step) > 3 else False, copy=False)
+            elif name == "num_op_sum":
+                apply_num_op_sum_evolution(sv, step[1], float(step[2]), norb, nelec, copy=False)
+            else:
+                raise ValueError(f"unknown step {name!r}: expected 'orbital_rotation', 'diag_coulomb' or 'num_op_sum'")
+        sv.set_layout(ROWS)  # the caller's buffer holds rows: same distribution out as in
+        finished = None
+        if host.size:
+            done = torch.cuda.Event()
+            done.record(main)
+            lane.s_out.wait_event(done)
+            sv.local.record_stream(lane.s_out)
+            _copy2d(out.ctypes.data, 16 * host.size, sv.local.data_ptr(), 16 * host.size, 16 * host.size, 1, _D2H,
+                    lane.s_out.cuda_stream)
+            finished = torch.cuda.Event()
+            finished.record(lane.s_out)
+    # the vector (and with it its symmetric-memory buffers) stays out of the pools until the result is collected
+    return HostEvolution(out, finished, (host, sv))
+
+
 def release_device_buffers() -> None:
     """Free the device state buffers the host pipeline keeps between calls."""
     torch.cuda.synchronize()

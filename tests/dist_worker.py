@@ -78,6 +78,21 @@ def main():
             norb=norb, nelec=nelec, n_steps=1, order=1)
         err = np.linalg.norm(out.gather().cpu().numpy() - want) / np.linalg.norm(want)
         assert err < tol, ("trotter", norb, nelec, err)
+        # host-resident shards: three overlapped applications of (rotation, diagonal Coulomb) on this rank's rows
+        from ffsim_b200.distributed import partition
+
+        dim_a, dim_b = models.dims(norb, nelec)
+        offs = partition(dim_a, world)
+        rank = dist.get_rank() if world > 1 else 0
+        rows = full.reshape(-1, dim_b)[offs[rank]:offs[rank + 1]]
+        steps = [("orbital_rotation", (ua, ub)), ("diag_coulomb", mat, 0.3)]
+        handles = [ffsim.evolve_host_rows_async(rows, steps, norb, nelec) for _ in range(3)]
+        want = gates.apply_diag_coulomb_evolution(cref.apply_orbital_rotation(full, (ua, ub), norb, nelec), mat, 0.3,
+                                                  norb, nelec).reshape(-1, dim_b)[offs[rank]:offs[rank + 1]]
+        for h in handles:
+            got = h.result().reshape(want.shape)
+            assert np.linalg.norm(got - want) <= tol * max(np.linalg.norm(want), 1e-300) + 1e-15, ("host rows", norb, nelec)
+        del handles, h
     hf = ShardedVector.hartree_fock(8, (4, 4), device=dev)
     assert abs(hf.norm() - 1) < 1e-15
     if world > 1 and os.environ.get("FFSIM_B200_REPORT_EXCHANGE"):
