@@ -314,6 +314,28 @@ def test_block_lists_are_ordered_for_conflict_free_gathers(norb, k, bound):
     assert extra <= bound * quarters, f"{extra} extra wavefronts in {quarters} quarter-warps"
 
 
+@pytest.mark.parametrize("norb, k, cols, bound", [(16, 5, 3, 1.25), (18, 7, 0, 1.20), (20, 8, 0, 1.22), (12, 6, 8, 1.001)])
+def test_gather_wavefronts_with_column_fastest_items(norb, k, cols, bound):
+    """The register-block gathers and scatters as the kernel walks them (32-item chunks, a quarter-warp per
+    shared-memory wavefront): with the items of a chunk ordered column-fastest (device_structs.h:
+    items_column_fastest) the wavefronts per conflict-free wavefront are 1.20 (C2), 1.14 (C3), 1.17 (C4), 1.00 (C1,
+    8 columns) -- and at least a tenth below the block-fastest walk of the same lists (1.40, 1.73, 1.54, 1.92)."""
+    hc = _hostcheck()
+    hc.ffb_hostcheck_gather_wavefronts.restype = ctypes.c_int
+    hc.ffb_hostcheck_gather_wavefronts.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                                   ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
+    rots, _ = givens_decomposition(rand.random_unitary(norb, seed=1))
+    q = (ctypes.c_int * len(rots))(*[min(int(r[2]), int(r[3])) for r in rots])
+    ratio = {}
+    for col_fast in (0, 1):
+        out = (ctypes.c_int64 * 2)()
+        assert hc.ffb_hostcheck_gather_wavefronts(norb, k, q, len(rots), cols, col_fast, out) == 0
+        assert out[1] > 1000
+        ratio[col_fast] = out[0] / out[1]
+    assert ratio[1] <= bound, ratio
+    assert ratio[1] <= 0.9 * ratio[0], ratio
+
+
 # ---------------------------------------------------------------- the kernel's index path, from the packed device tables
 def _emulate_device_view(norb, k, n_cols, smem, min_cols, sub_window, cols, nwarp, seed):
     from ffsim_b200.linalg.givens import _decompose_raw
