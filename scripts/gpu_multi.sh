@@ -1,5 +1,6 @@
 #!/bin/bash
-# multi-GPU check: sharded tests at N ranks (both exchanges) + the contract bench at N ranks (default exchange)
+# multi-GPU check: sharded tests at N ranks (both exchanges) + the contract bench at N ranks (default exchange);
+# C4 (254 GB, 8 ranks): torchrun --nproc-per-node 8 scripts/bench_sharded.py --norb 20 --nelec 8 8 --n-reps 3 --steps 2
 N=${1:-2}; TAG=${2:-r3m}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/${TAG}_gpus.txt
