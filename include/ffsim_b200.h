@@ -267,11 +267,15 @@ int ffb_memcpy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_
 int ffb_measure_fp64_peak(double *tflops);
 
 /* Tuning knobs (process-wide; read when a plan is built).  key/value pairs:
- *   "smem_bytes"   shared-memory budget per tile (default: device opt-in max)
- *   "min_cols"     smallest column strip per tile (default 4)
- *   "max_cols"     largest column strip (default 8)
+ *   "smem_bytes"   shared-memory budget per tile (default 220 KB)
+ *   "min_cols"     smallest column strip that may define the window width (default 3)
+ *   "max_cols"     largest column strip of a full-height tile (default 8)
  *   "sub_window"   register-block width, 2..6 (default 6)
- *   "threads"      CTA size of the fused pass kernel (default 512)
+ *   "threads"      CTA size of the fused pass kernel (default 512, the size it is built for)
+ *   "beta_mode"    beta side: 0 auto (in place when the sector fits one window, else a transposed copy with
+ *                  the transpositions folded into the first / last pass), 1 in place always, 2 transposed
+ *                  copy always, 3 transposed copy with separate transpose kernels
+ *   "bulk_copies"  1 (default): contiguous tile columns move as TMA bulk copies, 0: 16-byte copies only
  * Unknown keys return FFB_EINVAL. */
 int ffb_set_option(const char *key, int64_t value);
 int64_t ffb_get_option(const char *key);
