@@ -7,8 +7,13 @@ import json
 import os
 import sys
 
+import subprocess
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["FFSIM_B200_LIB"] = os.path.join(ROOT, "build", "dbg", "libffsim_b200.so")
+lib = os.path.join(ROOT, "build", "dbg", "libffsim_b200.so")
+if not os.path.exists(lib):
+    subprocess.run(["bash", os.path.join(ROOT, "scripts", "build_dbg.sh")], check=True, stdout=subprocess.DEVNULL)
+os.environ["FFSIM_B200_LIB"] = lib
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch
