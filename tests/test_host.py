@@ -380,3 +380,30 @@ def test_device_view_of_the_plan_tables(norb, k, n_cols, smem, min_cols, sub_win
     reproduce the oracle's rotation."""
     err = _emulate_device_view(norb, k, n_cols, smem, min_cols, sub_window, cols, nwarp, seed=100 * norb + k)
     assert err < 1e-13
+
+
+# ---------------------------------------------------------------- bench.py: the reference (CPU) arm's contract line
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` runs here (no GPU): exactly one line on stdout, a JSON object with the
+    contract's keys, the CPU baseline described, zero copy bytes; ranks other than 0 print nothing."""
+    import json
+    import subprocess
+    import sys
+
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c2", "--steps", "1",
+           "--warmup", "0"]
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    rec = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in rec, key
+    assert rec["impl"] == "reference" and rec["value"] > 0 and rec["unit"] == "applications/s"
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
+    assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["d2h_bytes_per_step"] == 0
+    assert "norb=16" in rec["config"]["workload"]
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
